@@ -1,0 +1,142 @@
+/* include/qscuda.h — C ABI of libqscuda.so, the B200 (sm_100a) implementation of the QuartetScores
+ * hot path: per-gene-tree distance matrices -> quartet topology counting -> LQ-IC / QP-IC / EQP-IC.
+ *
+ * The reference (lutteropp/QuartetScores @ f57c08b) has no FFI layer; the seam this ABI replaces is
+ * the C++ template class boundary between main() and QuartetScoreComputer<CINT>
+ * (src/QuartetScores.cpp:114-147 constructs it and calls four methods).  Each entry point below names
+ * the reference interface it stands in for (paths relative to the reference repository).
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 (QS_OK) or a
+ * negative QS_E* code and never throws; qs_last_error(ctx) gives a human-readable message for the
+ * last failure on that context.  Calls on one context must be serialised by the caller.  A context is
+ * bound to one CUDA device and owns all its device memory.  There is no CPU fallback: without a
+ * usable CUDA device qs_create fails with QS_E_CUDA.
+ *
+ * Taxon ("lookup") ids: position of the taxon in the reference tree's Euler-tour leaf order = left to
+ * right in its Newick text (src/QuartetCounterLookup.hpp:249-258).
+ * Table layout: QuartetLookupTable (src/quartet_lookup_table.hpp:135-212): entry of the quartet with
+ * sorted ids s0<s1<s2<s3 is at rank C(s3,4)+C(s2,3)+C(s1,2)+s0 and holds three CINT counters
+ * [#(s0s1|s2s3), #(s0s2|s1s3), #(s0s3|s1s2)].
+ */
+#ifndef QSCUDA_H
+#define QSCUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QS_ABI_VERSION 1
+
+enum {
+    QS_OK = 0,
+    QS_E_ARG = -1,          /* bad argument / call order */
+    QS_E_CUDA = -2,         /* CUDA runtime failure (message has the CUDA error string) */
+    QS_E_TREE = -3,         /* malformed tree encoding */
+    QS_E_REFERENCE = -4,    /* reference tree not usable (ids not in planar order, degree-2 inner node, ...) */
+    QS_E_MEMORY = -5,       /* table / matrices do not fit this device ("Insufficient memory!", QuartetScoreComputer.hpp:735-737) */
+    QS_E_UNSUPPORTED = -6,  /* valid input outside what this build handles (message says what) */
+    QS_E_STATE = -7         /* e.g. qs_score before qs_count */
+};
+
+/* mode for qs_create */
+enum {
+    QS_MODE_TABLE = 0,      /* keep the (sharded) count table resident: fast + qs_get_counts / qs_raw_qic possible */
+    QS_MODE_TABLE_FREE = 1  /* -s / savemem analogue: counts are scored as they are produced, no table */
+};
+
+typedef struct qs_ctx qs_ctx;
+
+/* Replaces: construction of QuartetScoreComputer<CINT> (src/QuartetScoreComputer.hpp:698-745) — CINT
+ * width selection (src/QuartetScores.cpp:115-147) is the caller's: cint_bytes in {1,2,4,8}.
+ * device: CUDA ordinal.  shard_index/shard_count: this context owns the quartets whose largest
+ * taxon id s3 lies in the shard's range (balanced split of the rank space by the outer index);
+ * use 0/1 for a single GPU. */
+int qs_create(qs_ctx** out, int n_taxa, int cint_bytes, int mode, int device, int shard_index, int shard_count);
+int qs_destroy(qs_ctx* ctx);
+const char* qs_last_error(const qs_ctx* ctx);
+const char* qs_strerror(int code);
+int qs_abi_version(void);
+
+/* Launch all work of this context on the given cudaStream_t (passed as void*; NULL = the context's
+ * own stream).  Lets a host framework time the kernels with its own events. */
+int qs_set_stream(qs_ctx* ctx, void* cuda_stream);
+
+/* Replaces: the reference-tree half of the QuartetScoreComputer / QuartetCounterLookup constructors
+ * (QuartetScoreComputer.hpp:710-718, QuartetCounterLookup.hpp:249-258, TreeInformation.hpp:95-113).
+ * Nodes are numbered as genesis numbers them (root 0, parent[i] < i), parent_edge[i] is the genesis
+ * edge index above node i (-1 for the root) so edge-indexed outputs line up with the Newick writer,
+ * children in Newick order through first_child/next_sibling, leaf_lookup_id[i] >= 0 exactly for leaves. */
+int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int32_t* parent_edge,
+                     const int32_t* leaf_lookup_id, const int32_t* first_child, const int32_t* next_sibling);
+
+/* Replaces: the per-tree part of QuartetCounterLookup::countQuartets (QuartetCounterLookup.hpp:202-221):
+ * the host flattens each evaluation tree while it parses (unknown taxon names are rejected there,
+ * where the reference throws, :218).  Tree t owns nodes [node_offsets[t], node_offsets[t+1]); inside a
+ * tree parent[i] < i (local indices), parent = -1 for the root, leaf_lookup_id >= 0 exactly for leaves,
+ * every id at most once per tree.  May be called repeatedly (streaming); host buffers are copied. */
+int qs_add_trees(qs_ctx* ctx, int n_trees, const int64_t* node_offsets, const int32_t* parent,
+                 const int32_t* leaf_lookup_id);
+int qs_clear_trees(qs_ctx* ctx);
+int qs_num_trees(const qs_ctx* ctx, int64_t* n_trees);
+
+/* Replaces: QuartetCounterLookup::countQuartets + updateQuartets* (QuartetCounterLookup.hpp:66-238) and
+ * the TreeInformation distance queries (TreeInformation.hpp:40-43) applied per gene tree.
+ * Builds every tree's n x n distance matrix on the device and counts, for every quartet of this
+ * shard and every tree, the displayed topology.  QS_MODE_TABLE leaves the table resident;
+ * QS_MODE_TABLE_FREE also accumulates the scoring partials (qs_count then implies the scan). */
+int qs_count(qs_ctx* ctx);
+
+/* Replaces: computeQuartetScoresBifurcating / processNodePair / computeQuartetScoresMultifurcating
+ * (QuartetScoreComputer.hpp:379-593) and getLQICScores/getQPICScores/getEQPICScores (:106-126).
+ * Each output has edge_count = n_nodes-1 doubles indexed by genesis edge index, +inf where untouched
+ * (:763,772-774).  For a multifurcating reference only lqic is computed; qpic/eqpic (may be NULL) are
+ * filled with +inf.  count_scale: 1 = the reference's runtime-efficient table semantics, 2 = its
+ * memory-efficient (-s) table, whose stored counts are doubled and wrap in CINT;
+ * the 32-bit wrap of the QP-IC accumulators (QuartetScoreComputer.hpp:382) is always reproduced unless
+ * exact_qp != 0.  With shard_count > 1 this returns the scores of this shard's quartets only; use
+ * qs_score_partials + qs_score_finalize around an all-reduce instead. */
+int qs_score(qs_ctx* ctx, int count_scale, int exact_qp, double* lqic, double* qpic, double* eqpic);
+
+/* Multi-GPU: partial results of this shard.  lqic_partial: edge_count doubles (min over this shard's
+ * quartets, +inf if none) -> all-reduce MIN.  pair_sums: 3 * n_pairs uint64 (sum over this shard's
+ * quartets of the three topology counts of every inner-node pair) -> all-reduce SUM.
+ * qs_score_finalize turns reduced partials into the three score vectors on the host. */
+int qs_score_num_pairs(const qs_ctx* ctx, int64_t* n_pairs);
+int qs_score_partials(qs_ctx* ctx, int count_scale, double* lqic_partial, uint64_t* pair_sums);
+int qs_score_finalize(qs_ctx* ctx, int exact_qp, const double* lqic_reduced, const uint64_t* pair_sums_reduced,
+                      double* lqic, double* qpic, double* eqpic);
+
+/* Parity hook for QuartetCounterLookup::countQuartetOccurrences (QuartetCounterLookup.hpp:300-318):
+ * canonical per-tree counts (1 per tree) of the entries [rank_begin, rank_end) in table layout, 3*cint_bytes
+ * per rank, copied to the host buffer `out`.  Ranks outside this shard read as zero.  QS_MODE_TABLE only. */
+int qs_get_counts(qs_ctx* ctx, uint64_t rank_begin, uint64_t rank_end, void* out);
+/* Rank range [begin,end) owned by this shard. */
+int qs_shard_range(const qs_ctx* ctx, uint64_t* rank_begin, uint64_t* rank_end);
+
+/* Parity hook for the distance kernel: tree t's matrix as n x n uint16 (0xFFFF = taxon missing). */
+int qs_get_distances(qs_ctx* ctx, int64_t tree, uint16_t* out);
+
+/* Replaces: printRawQICScores (QuartetScoreComputer.hpp:623-690).  Writes "(a,b|c,d): qic" lines in the
+ * reference's order and formatting; taxon_names[id] is the label of lookup id `id`.  QS_MODE_TABLE,
+ * single shard only. */
+int qs_write_raw_qic(qs_ctx* ctx, int count_scale, const char* const* taxon_names, const char* path);
+
+/* Device timing of the last qs_count / scoring pass (CUDA events on the context's stream), and the
+ * number of kernels this library launched since the context was created. */
+int qs_last_timing(const qs_ctx* ctx, double* dist_ms, double* count_ms, double* score_ms);
+int qs_launch_count(const qs_ctx* ctx, int64_t* n_launches);
+
+/* Live micro-benchmark of the issue rate the counting kernel is bound by: packed fp16x2
+ * compare (HSET2) + accumulate (HADD2) lane-operations per second on this device, and the plain
+ * int32 IADD3/LOP3 rate, both measured with the clocks the device sustains right now.  Used as the
+ * roofline denominator in bench.py. */
+int qs_measure_alu_peak(qs_ctx* ctx, double* half2_pair_laneops_per_s, double* int32_laneops_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QSCUDA_H */

@@ -1,0 +1,131 @@
+// dist.cuh — per-gene-tree topological distance matrices.
+//
+// Reference semantics: TreeInformation::distanceInEdges (src/TreeInformation.hpp:40-43):
+// d(u,v) = depth[u] + depth[v] - 2*depth[lca(u,v)], with the LCA from an Euler tour + RMQ
+// (:71-76,95-113).  The reference applies it to the reference tree only; the B200 design applies the
+// same formula to every gene tree and feeds the counting kernel with the n x n matrices.
+//
+// One CTA per tree (grid-stride).  Flat tree encoding -> (a) depths and an Euler-tour leaf sequence
+// (one thread, O(N); the tree is tiny), (b) all leaf pairs in parallel: the LCA depth of the leaves at
+// tour positions i<j is the minimum of the "turning depths" h[i..j-1] between consecutive leaves, taken
+// as a running minimum while all lanes sweep the same j so that stores go to one matrix row.
+//
+// Output: D[tree][row][col] as IEEE fp16 (exact for integers <= 2048), NaN where either taxon is
+// absent from the tree (the buffer is pre-filled with 0xFFFF = NaN), row pitch n_pad (multiple of 8).
+#pragma once
+#include "common.cuh"
+
+namespace qs {
+
+struct DistArgs {
+    const int64_t* node_off;   // [m+1]
+    const int32_t* parent;     // concatenated, local indices, parent[i] < i
+    const int32_t* leaf_id;    // lookup id or -1
+    int m, n, n_pad, max_nodes;
+    __half* D;
+    int* max_dist;             // [0] global max over all trees (atomicMax), [1] first tree-encoding error code
+};
+
+__global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
+    extern __shared__ int32_t sm_i[];
+    const int NMAX = a.max_nodes;
+    int32_t* par = sm_i;              // [NMAX]
+    int32_t* fc = par + NMAX;         // first child / DFS iterator
+    int32_t* ns = fc + NMAX;          // next sibling
+    int32_t* dep = ns + NMAX;         // depth
+    int32_t* stk = dep + NMAX;        // DFS stack
+    int32_t* ltid = stk + NMAX;       // per leaf (tour order): taxon id
+    int32_t* ldep = ltid + NMAX;      // depth
+    int32_t* lh = ldep + NMAX;        // lh[i] = depth of lca(leaf i, leaf i+1)
+    uint32_t* seen = reinterpret_cast<uint32_t*>(lh + NMAX);   // [(n+31)/32] taxon bitmap (duplicate check)
+    __shared__ int s_k;
+    int local_max = 0;
+
+    for (int t = blockIdx.x; t < a.m; t += gridDim.x) {
+        const int64_t off = a.node_off[t];
+        const int N = (int)(a.node_off[t + 1] - off);
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) { par[i] = a.parent[off + i]; fc[i] = -1; ns[i] = -1; }
+        for (int i = threadIdx.x; i < (a.n + 31) / 32; i += blockDim.x) seen[i] = 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int bad = 0;
+            dep[0] = 0;
+            for (int i = 1; i < N; ++i) { if (par[i] < 0 || par[i] >= i) { bad = 1; par[i] = 0; } }
+            for (int i = 1; i < N; ++i) dep[i] = dep[par[i]] + 1;
+            for (int i = N - 1; i >= 1; --i) { int p = par[i]; ns[i] = fc[p]; fc[p] = i; }
+            int k = 0, sp = 0, cur_min = 0x7fffffff;
+            if (N > 0 && fc[0] == -1) {                       // single-node tree
+                int id = a.leaf_id[off];
+                if (id >= 0 && id < a.n) { ltid[0] = id; ldep[0] = 0; k = 1; } else bad = 2;
+            } else if (N > 0) {
+                stk[sp++] = 0;
+                while (sp > 0) {
+                    int v = stk[sp - 1];
+                    int c = fc[v];
+                    if (c == -1) { --sp; continue; }
+                    fc[v] = ns[c];                            // advance iterator
+                    cur_min = min(cur_min, dep[v]);           // v is a turning point on the way to the next leaf
+                    if (fc[c] == -1) {                        // leaf
+                        if (k > 0) lh[k - 1] = cur_min;
+                        int id = a.leaf_id[off + c];
+                        if (id < 0 || id >= a.n) { bad = 2; id = 0; }
+                        else if (seen[id >> 5] & (1u << (id & 31))) bad = 3;
+                        else seen[id >> 5] |= 1u << (id & 31);
+                        ltid[k] = id; ldep[k] = dep[c]; ++k;
+                        cur_min = 0x7fffffff;
+                    } else {
+                        if (a.leaf_id[off + c] >= 0) bad = 4;   // inner node carrying a taxon id
+                        stk[sp++] = c;
+                    }
+                }
+            }
+            if (bad) { atomicCAS(a.max_dist + 1, 0, bad); k = 0; }
+            s_k = k;
+        }
+        __syncthreads();
+        const int k = s_k;
+        __half* Dt = a.D + (size_t)t * a.n * a.n_pad;
+        for (int i0 = 0; i0 < k; i0 += blockDim.x) {
+            const int i = i0 + threadIdx.x;
+            const bool act = i < k;
+            const int ti = act ? ltid[i] : 0, di = act ? ldep[i] : 0;
+            if (act) Dt[(size_t)ti * a.n_pad + ti] = __int2half_rn(0);
+            // sweep 1: j ascending, lanes with i < j
+            int mn = 0x7fffffff;
+            const int jlo = i0 + 1;                           // first j any lane of this block-iteration needs
+            for (int j = jlo; j < k; ++j) {
+                if (act && j > i) {
+                    mn = min(mn, lh[j - 1]);
+                    int d = di + ldep[j] - 2 * mn;
+                    local_max = max(local_max, d);
+                    Dt[(size_t)ltid[j] * a.n_pad + ti] = __int2half_rn(d);
+                }
+            }
+            // sweep 2: j descending, lanes with i > j
+            mn = 0x7fffffff;
+            const int jhi = min(k - 1, i0 + (int)blockDim.x - 1) - 1;
+            for (int j = jhi; j >= 0; --j) {
+                if (act && j < i) {
+                    mn = min(mn, lh[j]);
+                    int d = di + ldep[j] - 2 * mn;
+                    Dt[(size_t)ltid[j] * a.n_pad + ti] = __int2half_rn(d);
+                }
+            }
+        }
+    }
+    // block max -> global
+    for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
+    if ((threadIdx.x & 31) == 0 && local_max > 0) atomicMax(a.max_dist, local_max);
+}
+
+// fp16 matrix of one tree -> uint16 (0xFFFF for NaN): parity hook qs_get_distances
+__global__ void qs_dist_to_u16_kernel(const __half* Dt, int n, int n_pad, uint16_t* out) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * n) return;
+    int r = idx / n, c = idx % n;
+    __half h = Dt[(size_t)r * n_pad + c];
+    out[idx] = __hisnan(h) ? (uint16_t)0xFFFF : (uint16_t)__half2int_rn(h);
+}
+
+}  // namespace qs

@@ -1,0 +1,846 @@
+// qscuda.cu — host side of libqscuda.so: context, C ABI (include/qscuda.h), kernel orchestration.
+//
+// B200-native (sm_100a) re-design of the QuartetScores hot path (reference: lutteropp/QuartetScores,
+// src/QuartetCounterLookup.hpp, src/quartet_lookup_table.hpp, src/TreeInformation.hpp,
+// src/QuartetScoreComputer.hpp).  There is no CPU fallback in this file: every count and every
+// per-quartet QIC selection happens in the CUDA kernels under kernels/.
+#include "../../include/qscuda.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <limits>
+#include <string>
+#include <vector>
+
+#include "kernels/common.cuh"
+#include "kernels/count_small.cuh"
+#include "kernels/count_tiled.cuh"
+#include "kernels/dist.cuh"
+#include "kernels/score.cuh"
+#include "kernels/ubench.cuh"
+
+using namespace qs;
+
+namespace {
+
+constexpr int kMaxHalfExact = 2048;     // integers up to 2048 are exact in fp16
+constexpr int kSmallThreads = 512;
+
+struct HostRef {
+    int n_nodes = 0, n_inner = 0;
+    bool bifurcating = false;
+    std::vector<int32_t> parent, parent_edge, leaf_id, first_child, next_sib, depth, inner_index, inner_node, leaf_node;
+    std::vector<uint16_t> lca;          // [n][n] inner index
+    std::vector<uint16_t> idepth;       // [I]
+};
+
+}  // namespace
+
+struct qs_ctx {
+    int device = 0, n = 0, n_pad = 0, cint_bytes = 2, mode = 0, shard_index = 0, shard_count = 1;
+    int d_begin = 0, d_end = 0, num_sms = 148, smem_optin = 0;
+    uint64_t rank_begin = 0, rank_end = 0;
+    std::string err;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int64_t launches = 0;
+    double dist_ms = 0, count_ms = 0, score_ms = 0;
+
+    bool has_ref = false;
+    HostRef ref;
+    uint16_t* d_lca = nullptr;
+    uint16_t* d_idepth = nullptr;
+    int64_t* d_PB = nullptr;
+    int64_t score_blocks = 0;
+
+    // trees
+    int64_t m = 0, total_nodes = 0, cap_nodes = 0, cap_trees = 0;
+    int max_nodes = 0;
+    std::vector<int64_t> h_off{0};
+    int64_t* d_off = nullptr;
+    int32_t* d_parent = nullptr;
+    int32_t* d_leaf = nullptr;
+
+    // distances
+    __half* d_D = nullptr;
+    size_t D_cap = 0;
+    int* d_flags = nullptr;      // [0] max distance, [1] tree error
+    bool dist_valid = false;
+
+    // counting
+    uint32_t* d_ws = nullptr;
+    void* d_table = nullptr;
+    size_t table_elems = 0;
+    int32_t *d_PX = nullptr, *d_PY = nullptr, *d_CD = nullptr;
+    int NX = 0, NY = 0;
+    bool counted = false;
+
+    // scoring
+    unsigned long long* d_pair_sums = nullptr;
+    unsigned long long* d_pair_best = nullptr;
+    std::vector<unsigned long long> h_pair_sums, h_pair_best;
+    bool fused_partials_valid = false;   // table-free mode: partials accumulated by qs_count
+    int fused_scale = 0;
+};
+
+namespace {
+
+#define QS_FAIL(ctx, code, ...)                       \
+    do {                                              \
+        char _b[512];                                 \
+        snprintf(_b, sizeof(_b), __VA_ARGS__);        \
+        (ctx)->err = _b;                              \
+        return (code);                                \
+    } while (0)
+
+#define QS_CUDA(ctx, call)                                                                                   \
+    do {                                                                                                     \
+        cudaError_t _e = (call);                                                                             \
+        if (_e != cudaSuccess) QS_FAIL(ctx, QS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+template <typename T>
+int dev_alloc(qs_ctx* c, T** p, size_t count) {
+    if (*p) { cudaFree(*p); *p = nullptr; }
+    if (count == 0) return QS_OK;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        QS_FAIL(c, QS_E_MEMORY, "Insufficient memory! cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    }
+    return QS_OK;
+}
+
+// balanced split of the rank space by the outer index d: boundaries ~ n * (g/G)^(1/4), rounded to 8
+void shard_bounds(int n, int g, int G, int* d_begin, int* d_end) {
+    auto bound = [&](int i) -> int {
+        if (i <= 0) return 3;
+        if (i >= G) return n;
+        double x = (double)n * pow((double)i / G, 0.25);
+        int v = ((int)(x + 4.0) / 8) * 8;
+        return std::min(n, std::max(3, v));
+    };
+    *d_begin = bound(g);
+    *d_end = bound(g + 1);
+    if (*d_end < *d_begin) *d_end = *d_begin;
+}
+
+double host_log_score(uint64_t q1, uint64_t q2, uint64_t q3) {
+    // src/QuartetScoreComputer.hpp:135-159 — evaluated on the HOST with the same libm and operation
+    // order as the reference; only applied to integer results produced on the GPU.
+    if (q1 == 0 && q2 == 0 && q3 == 0) return 0;
+    uint64_t sum = q1 + q2 + q3;
+    double p1 = (double)q1 / sum, p2 = (double)q2 / sum, p3 = (double)q3 / sum;
+    double qic = 1;
+    if (p1 != 0) qic += p1 * log(p1) / log(3);
+    if (p2 != 0) qic += p2 * log(p2) / log(3);
+    if (p3 != 0) qic += p3 * log(p3) / log(3);
+    if (q1 < q2 || q1 < q3) return qic * -1;
+    return qic;
+}
+
+uint64_t cint_mask(int bytes) { return bytes >= 8 ? ~0ull : ((1ull << (8 * bytes)) - 1); }
+
+void free_all(qs_ctx* c) {
+    cudaFree(c->d_lca); cudaFree(c->d_idepth); cudaFree(c->d_PB);
+    cudaFree(c->d_off); cudaFree(c->d_parent); cudaFree(c->d_leaf);
+    cudaFree(c->d_D); cudaFree(c->d_flags); cudaFree(c->d_ws); cudaFree(c->d_table);
+    cudaFree(c->d_PX); cudaFree(c->d_PY); cudaFree(c->d_CD);
+    cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+}
+
+// does the whole-matrix kernel apply?  two stages of at least one tree each must fit in shared memory
+bool small_path_ok(const qs_ctx* c) {
+    size_t tree_bytes = (size_t)c->n * c->n_pad * 2;
+    return 128 + 2 * tree_bytes <= (size_t)c->smem_optin;
+}
+
+// ---- item enumeration tables of the whole-matrix counting kernel (see kernels/count_small.cuh) -----
+int build_small_tables(qs_ctx* c) {
+    const int n = c->n;
+    std::vector<int32_t> PX(n + 1, 0), PY(n + 1, 0), CD(n + 1, 0);
+    int64_t acc = 0;
+    for (int cc = 0; cc < n; ++cc) {
+        PX[cc] = (int32_t)acc;
+        if (cc >= 2) {
+            int dlo = std::max(cc + 1, c->d_begin);
+            int64_t nd = std::max(0, c->d_end - dlo);
+            int64_t nb = (cc + 7) / 8;
+            acc += nb * (nb + 1) / 2 * nd;
+        }
+    }
+    PX[n] = (int32_t)acc;
+    if (acc > 0x7fffffff) QS_FAIL(c, QS_E_UNSUPPORTED, "item count overflow");
+    c->NX = (int)acc;
+    acc = 0;
+    for (int cc = 0; cc < n; ++cc) {
+        CD[cc] = (int32_t)acc;
+        if (cc >= 2) {
+            int dlo = std::max(cc + 1, c->d_begin);
+            if (dlo < c->d_end) acc += (c->d_end - 1) / 8 - dlo / 8 + 1;
+        }
+    }
+    CD[n] = (int32_t)acc;
+    acc = 0;
+    for (int b = 0; b < n; ++b) {
+        PY[b] = (int32_t)acc;
+        if (b >= 1 && b + 1 < n) {
+            int64_t na = (b + 7) / 8;
+            int64_t chunks = CD[n] - CD[b + 1];
+            acc += na * chunks;
+        }
+    }
+    PY[n] = (int32_t)acc;
+    if (acc > 0x7fffffff) QS_FAIL(c, QS_E_UNSUPPORTED, "item count overflow");
+    c->NY = (int)acc;
+    int r;
+    if ((r = dev_alloc(c, &c->d_PX, n + 1))) return r;
+    if ((r = dev_alloc(c, &c->d_PY, n + 1))) return r;
+    if ((r = dev_alloc(c, &c->d_CD, n + 1))) return r;
+    QS_CUDA(c, cudaMemcpy(c->d_PX, PX.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_PY, PY.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_CD, CD.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
+    return QS_OK;
+}
+
+template <typename CINT>
+void launch_narrow(qs_ctx* c, uint64_t elems) {
+    int blocks = (int)std::min<uint64_t>((elems + 255) / 256, (uint64_t)c->num_sms * 16);
+    if (blocks < 1) blocks = 1;
+    qs_narrow_kernel<CINT><<<blocks, 256, 0, c->stream>>>(c->d_ws, (CINT*)c->d_table, elems);
+    c->launches++;
+}
+
+template <typename CINT>
+void launch_score(qs_ctx* c, const ScoreArgs& a) {
+    qs_score_table_kernel<CINT><<<(unsigned)c->score_blocks, 128, 0, c->stream>>>(a);
+    c->launches++;
+}
+
+int run_distances(qs_ctx* c) {
+    const size_t need = (size_t)c->m * c->n * c->n_pad;
+    if (need > c->D_cap) {
+        int r = dev_alloc(c, &c->d_D, need);
+        if (r) { c->D_cap = 0; return r; }
+        c->D_cap = need;
+    }
+    QS_CUDA(c, cudaMemsetAsync(c->d_D, 0xFF, need * sizeof(__half), c->stream));   // 0xFFFF = NaN = "taxon missing"
+    QS_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(int), c->stream));
+    DistArgs da;
+    da.node_off = c->d_off; da.parent = c->d_parent; da.leaf_id = c->d_leaf;
+    da.m = (int)c->m; da.n = c->n; da.n_pad = c->n_pad; da.max_nodes = c->max_nodes; da.D = c->d_D; da.max_dist = c->d_flags;
+    size_t smem = (size_t)8 * 4 * c->max_nodes + (size_t)((c->n + 31) / 32) * 4;
+    if (smem > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "gene tree with %d nodes exceeds the distance kernel's shared-memory budget", c->max_nodes);
+    QS_CUDA(c, cudaFuncSetAttribute(qs_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = std::max(1, std::min(8, (int)((size_t)c->smem_optin / std::max<size_t>(smem, 1024))));
+    int grid = (int)std::min<int64_t>(c->m, (int64_t)c->num_sms * per_sm);
+    qs_dist_kernel<<<grid, 256, smem, c->stream>>>(da);
+    c->launches++;
+    QS_CUDA(c, cudaGetLastError());
+    c->dist_valid = true;
+    return QS_OK;
+}
+
+int run_count_small(qs_ctx* c) {
+    int r;
+    if (!c->d_PX && (r = build_small_tables(c))) return r;
+    const uint64_t nq = c->rank_end - c->rank_begin;
+    if (!c->d_ws && (r = dev_alloc(c, &c->d_ws, (size_t)nq * 3))) return r;
+    QS_CUDA(c, cudaMemsetAsync(c->d_ws, 0, (size_t)nq * 3 * sizeof(uint32_t), c->stream));
+    CountSmallArgs a;
+    a.D = c->d_D; a.ws = c->d_ws; a.PX = c->d_PX; a.PY = c->d_PY; a.CD = c->d_CD;
+    a.rank_base = c->rank_begin; a.n = c->n; a.n_pad = c->n_pad; a.m = (int)c->m;
+    a.d_begin = c->d_begin; a.d_end = c->d_end; a.NX = c->NX; a.NY = c->NY;
+    a.tree_bytes = (uint32_t)((size_t)c->n * c->n_pad * 2);
+    a.n_item_blocks = (std::max(c->NX, c->NY) + kSmallThreads - 1) / kSmallThreads;
+    if (a.n_item_blocks == 0) return QS_OK;
+    int tps = (int)(((size_t)c->smem_optin - 128) / (2 * (size_t)a.tree_bytes));
+    tps = std::max(1, std::min(tps, 8));
+    a.trees_per_stage = tps;
+    // tree chunks: <= 2048 trees each (fp16 counters), and enough tasks to fill whole waves of SMs
+    const int s_min = (int)((c->m + kMaxHalfExact - 1) / kMaxHalfExact);
+    int best_s = s_min; double best_eff = -1;
+    for (int s = s_min; s <= s_min + 12 && s <= std::max<int64_t>(1, c->m); ++s) {
+        int64_t tasks = (int64_t)a.n_item_blocks * s;
+        int64_t waves = (tasks + c->num_sms - 1) / c->num_sms;
+        double eff = (double)tasks / (double)(waves * c->num_sms);
+        if (eff > best_eff + 0.02) { best_eff = eff; best_s = s; }
+    }
+    int chunk = (int)((c->m + best_s - 1) / best_s);
+    chunk = std::min(kMaxHalfExact, ((chunk + tps - 1) / tps) * tps);
+    a.chunk_trees = chunk;
+    a.n_tree_chunks = (int)((c->m + chunk - 1) / chunk);
+    size_t smem = 128 + (size_t)CS_STAGES * tps * a.tree_bytes;
+    QS_CUDA(c, cudaFuncSetAttribute(qs_count_small_kernel<kSmallThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int grid = std::min(a.n_item_blocks * a.n_tree_chunks, c->num_sms);
+    qs_count_small_kernel<kSmallThreads><<<grid, kSmallThreads, smem, c->stream>>>(a);
+    c->launches++;
+    QS_CUDA(c, cudaGetLastError());
+    // workspace -> CINT table
+    const uint64_t elems = nq * 3;
+    switch (c->cint_bytes) {
+        case 1: launch_narrow<uint8_t>(c, elems); break;
+        case 2: launch_narrow<uint16_t>(c, elems); break;
+        case 4: launch_narrow<uint32_t>(c, elems); break;
+        default: launch_narrow<unsigned long long>(c, elems); break;
+    }
+    QS_CUDA(c, cudaGetLastError());
+    return QS_OK;
+}
+
+int run_count_tiled(qs_ctx* c) {
+    QS_FAIL(c, QS_E_UNSUPPORTED, "n = %d taxa needs the tiled counting kernel, which this build does not have yet", c->n);
+}
+
+int build_reference(qs_ctx* c, int n_nodes, const int32_t* parent, const int32_t* parent_edge, const int32_t* leaf_id,
+                    const int32_t* first_child, const int32_t* next_sibling) {
+    HostRef& R = c->ref;
+    R = HostRef();
+    if (n_nodes < 5 || n_nodes > 65535) QS_FAIL(c, QS_E_REFERENCE, "reference tree has %d nodes (need 5..65535)", n_nodes);
+    R.n_nodes = n_nodes;
+    R.parent.assign(parent, parent + n_nodes); R.parent_edge.assign(parent_edge, parent_edge + n_nodes);
+    R.leaf_id.assign(leaf_id, leaf_id + n_nodes); R.first_child.assign(first_child, first_child + n_nodes);
+    R.next_sib.assign(next_sibling, next_sibling + n_nodes);
+    R.depth.assign(n_nodes, 0);
+    if (parent[0] != -1) QS_FAIL(c, QS_E_REFERENCE, "node 0 must be the root");
+    std::vector<int> nchild(n_nodes, 0);
+    for (int i = 1; i < n_nodes; ++i) {
+        if (parent[i] < 0 || parent[i] >= i) QS_FAIL(c, QS_E_REFERENCE, "parent[%d] = %d violates parent < child numbering", i, parent[i]);
+        if (parent_edge[i] < 0 || parent_edge[i] >= n_nodes - 1) QS_FAIL(c, QS_E_REFERENCE, "parent_edge[%d] out of range", i);
+        R.depth[i] = R.depth[parent[i]] + 1;
+        nchild[parent[i]]++;
+    }
+    // child lists must be consistent with parent[]
+    for (int v = 0; v < n_nodes; ++v) {
+        int cnt = 0;
+        for (int ch = first_child[v]; ch != -1; ch = next_sibling[ch]) {
+            if (ch <= v || ch >= n_nodes || parent[ch] != v || ++cnt > nchild[v]) QS_FAIL(c, QS_E_REFERENCE, "child list of node %d inconsistent with parent[]", v);
+        }
+        if (cnt != nchild[v]) QS_FAIL(c, QS_E_REFERENCE, "child list of node %d inconsistent with parent[]", v);
+        if ((nchild[v] == 0) != (leaf_id[v] >= 0)) QS_FAIL(c, QS_E_REFERENCE, "leaf_lookup_id must be >= 0 exactly for leaves (node %d)", v);
+    }
+    // planar (Euler tour) leaf order must be 0,1,2,...  (QuartetCounterLookup.hpp:249-258)
+    const int n = c->n;
+    R.leaf_node.assign(n, -1);
+    std::vector<int> lo(n_nodes, 0), hi(n_nodes, 0);
+    {
+        int k = 0;
+        std::vector<int> stack{0}, it(n_nodes);
+        for (int v = 0; v < n_nodes; ++v) it[v] = first_child[v];
+        lo[0] = 0;
+        while (!stack.empty()) {
+            int v = stack.back();
+            int ch = it[v];
+            if (ch == -1) { hi[v] = k; stack.pop_back(); continue; }
+            it[v] = next_sibling[ch];
+            lo[ch] = k;
+            if (first_child[ch] == -1) {
+                if (k >= n || leaf_id[ch] != k) QS_FAIL(c, QS_E_REFERENCE, "lookup ids must follow the reference tree's Euler-tour leaf order (leaf %d has id %d)", k, leaf_id[ch]);
+                R.leaf_node[k] = ch; ++k; hi[ch] = k;
+            } else stack.push_back(ch);
+        }
+        if (k != n) QS_FAIL(c, QS_E_REFERENCE, "reference tree has %d leaves, context was created for %d taxa", k, n);
+    }
+    // genesis is_bifurcating: max rank (links - 1) == 2 (genesis tree/function/functions.cpp:57-69)
+    int max_rank = 0; bool all3 = true;
+    R.inner_index.assign(n_nodes, -1);
+    for (int v = 0; v < n_nodes; ++v) {
+        int links = nchild[v] + (v != 0 ? 1 : 0);
+        max_rank = std::max(max_rank, links - 1);
+        if (nchild[v] > 0) {
+            R.inner_index[v] = (int)R.inner_node.size();
+            R.inner_node.push_back(v);
+            if (links != 3) all3 = false;
+        }
+    }
+    R.n_inner = (int)R.inner_node.size();
+    R.bifurcating = (max_rank == 2);
+    if (R.bifurcating && !all3)
+        QS_FAIL(c, QS_E_REFERENCE, "reference tree passes is_bifurcating but has an inner node of degree 2 (e.g. a rooted tree); the reference mis-scores such trees (SURVEY.md App. B6) - unroot it");
+    // LCA of every leaf pair (inner index) and inner depths
+    R.lca.assign((size_t)n * n, 0);
+    R.idepth.resize(R.n_inner);
+    for (int v = 0; v < n_nodes; ++v) {
+        if (nchild[v] == 0) continue;
+        const uint16_t iv = (uint16_t)R.inner_index[v];
+        R.idepth[iv] = (uint16_t)R.depth[v];
+        for (int c1 = first_child[v]; c1 != -1; c1 = next_sibling[c1])
+            for (int c2 = next_sibling[c1]; c2 != -1; c2 = next_sibling[c2])
+                for (int x = lo[c1]; x < hi[c1]; ++x)
+                    for (int y = lo[c2]; y < hi[c2]; ++y) { R.lca[(size_t)x * n + y] = iv; R.lca[(size_t)y * n + x] = iv; }
+    }
+    return QS_OK;
+}
+
+// per-b block prefix of the table scan (kernels/score.cuh): thread = (c,d) pair, d in the shard range
+int build_score_blocks(qs_ctx* c) {
+    const int n = c->n;
+    std::vector<int64_t> PB(n + 1, 0);
+    int64_t acc = 0;
+    for (int b = 0; b < n; ++b) {
+        PB[b] = acc;
+        if (b >= 1 && b <= n - 3) {
+            int dlo = std::max(b + 2, c->d_begin);
+            if (dlo < c->d_end) {
+                int64_t k0 = dlo - b - 1, k1 = c->d_end - b - 1;       // pairs = sum_{k=k0}^{k1-1} k
+                int64_t pairs = k1 * (k1 - 1) / 2 - k0 * (k0 - 1) / 2;
+                acc += (pairs + 127) / 128;
+            }
+        }
+    }
+    PB[n] = acc;
+    c->score_blocks = acc;
+    if (acc > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "score grid too large");
+    int r;
+    if ((r = dev_alloc(c, &c->d_PB, n + 1))) return r;
+    QS_CUDA(c, cudaMemcpy(c->d_PB, PB.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
+    return QS_OK;
+}
+
+int ensure_pair_arrays(qs_ctx* c) {
+    const size_t I = c->ref.n_inner;
+    int r;
+    if (!c->d_pair_sums && (r = dev_alloc(c, &c->d_pair_sums, I * I * 3))) return r;
+    if (!c->d_pair_best && (r = dev_alloc(c, &c->d_pair_best, I * I))) return r;
+    return QS_OK;
+}
+
+// scan the resident table on the device -> per-pair partials on the host
+int run_score_scan(qs_ctx* c, int count_scale) {
+    if (!c->has_ref) QS_FAIL(c, QS_E_STATE, "qs_set_reference has not been called");
+    if (!c->counted) QS_FAIL(c, QS_E_STATE, "qs_count has not been called");
+    if (count_scale != 1 && count_scale != 2) QS_FAIL(c, QS_E_ARG, "count_scale must be 1 or 2");
+    const size_t I = c->ref.n_inner;
+    int r;
+    if (c->mode == QS_MODE_TABLE_FREE) {
+        if (!c->fused_partials_valid || c->fused_scale != count_scale)
+            QS_FAIL(c, QS_E_STATE, "table-free context: partials were accumulated by qs_count with count_scale=%d", c->fused_scale);
+    } else {
+        if ((r = ensure_pair_arrays(c))) return r;
+        if (!c->d_PB && (r = build_score_blocks(c))) return r;
+        QS_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
+        QS_CUDA(c, cudaMemsetAsync(c->d_pair_sums, 0, I * I * 3 * 8, c->stream));
+        QS_CUDA(c, cudaMemsetAsync(c->d_pair_best, 0xFF, I * I * 8, c->stream));
+        if (c->score_blocks > 0) {
+            ScoreArgs a;
+            a.table = c->d_table; a.rank_base = c->rank_begin; a.lca = c->d_lca; a.idepth = c->d_idepth;
+            a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.PB = c->d_PB; a.n = c->n; a.I = (int)I;
+            a.d_begin = c->d_begin; a.d_end = c->d_end; a.count_scale = count_scale; a.cint_mask = cint_mask(c->cint_bytes);
+            a.bifurcating = c->ref.bifurcating ? 1 : 0;
+            switch (c->cint_bytes) {
+                case 1: launch_score<uint8_t>(c, a); break;
+                case 2: launch_score<uint16_t>(c, a); break;
+                case 4: launch_score<uint32_t>(c, a); break;
+                default: launch_score<unsigned long long>(c, a); break;
+            }
+            QS_CUDA(c, cudaGetLastError());
+        }
+        QS_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+    }
+    c->h_pair_sums.resize(I * I * 3);
+    c->h_pair_best.resize(I * I);
+    QS_CUDA(c, cudaMemcpyAsync(c->h_pair_sums.data(), c->d_pair_sums, I * I * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
+    QS_CUDA(c, cudaMemcpyAsync(c->h_pair_best.data(), c->d_pair_best, I * I * 8, cudaMemcpyDeviceToHost, c->stream));
+    QS_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (c->mode != QS_MODE_TABLE_FREE) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
+        c->score_ms = ms;
+    }
+    return QS_OK;
+}
+
+template <typename F>
+void for_path_edges(const HostRef& R, int u, int v, F f) {
+    while (u != v) {
+        if (R.depth[u] >= R.depth[v]) { f(R.parent_edge[u]); u = R.parent[u]; }
+        else { f(R.parent_edge[v]); v = R.parent[v]; }
+    }
+}
+
+// LQ-IC partial of this shard: exact (host libm) QIC of each pair's selected quartet, min over path edges
+void lqic_from_pairs(const qs_ctx* c, double* lqic) {
+    const HostRef& R = c->ref;
+    const int I = R.n_inner, E = R.n_nodes - 1;
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int e = 0; e < E; ++e) lqic[e] = inf;
+    const uint64_t M = (1ull << QS_TRIPLE_BITS) - 1;
+    for (int iu = 0; iu < I; ++iu)
+        for (int iv = iu + 1; iv < I; ++iv) {
+            const unsigned long long t = c->h_pair_best[(size_t)iu * I + iv];
+            if (t == QS_TRIPLE_NONE) continue;
+            const double qic = host_log_score(t >> (2 * QS_TRIPLE_BITS), (t >> QS_TRIPLE_BITS) & M, t & M);
+            for_path_edges(R, R.inner_node[iu], R.inner_node[iv], [&](int e) { if (qic < lqic[e]) lqic[e] = qic; });
+        }
+}
+
+// QP-IC / EQP-IC from (reduced) pair sums: QuartetScoreComputer.hpp:472-489
+void qp_from_pairs(const qs_ctx* c, const uint64_t* sums, int exact_qp, double* qpic, double* eqpic) {
+    const HostRef& R = c->ref;
+    const int I = R.n_inner, E = R.n_nodes - 1;
+    const double inf = std::numeric_limits<double>::infinity();
+    for (int e = 0; e < E; ++e) { if (qpic) qpic[e] = inf; if (eqpic) eqpic[e] = inf; }
+    if (!R.bifurcating) return;
+    for (int iu = 0; iu < I; ++iu)
+        for (int iv = iu + 1; iv < I; ++iv) {
+            const uint64_t* s = sums + ((size_t)iu * I + iv) * 3;
+            uint64_t p1 = s[0], p2 = s[1], p3 = s[2];
+            if (!exact_qp) { p1 &= 0xffffffffull; p2 &= 0xffffffffull; p3 &= 0xffffffffull; }   // `unsigned p1,p2,p3` (:382)
+            const double qp = host_log_score(p1, p2, p3);
+            const int u = R.inner_node[iu], v = R.inner_node[iv];
+            // :475-481 adjacency through the primary links (for the root: its first child link)
+            const int u_outer = (u == 0) ? R.first_child[0] : R.parent[u];
+            const int v_outer = (v == 0) ? R.first_child[0] : R.parent[v];
+            if (qpic) {
+                if (u_outer == v) qpic[(u == 0) ? R.parent_edge[v] : R.parent_edge[u]] = qp;
+                else if (v_outer == u) qpic[(v == 0) ? R.parent_edge[u] : R.parent_edge[v]] = qp;
+            }
+            if (eqpic) for_path_edges(R, u, v, [&](int e) { if (qp < eqpic[e]) eqpic[e] = qp; });
+        }
+}
+
+}  // namespace
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+
+extern "C" {
+
+int qs_abi_version(void) { return QS_ABI_VERSION; }
+
+const char* qs_strerror(int code) {
+    switch (code) {
+        case QS_OK: return "ok";
+        case QS_E_ARG: return "bad argument";
+        case QS_E_CUDA: return "CUDA failure";
+        case QS_E_TREE: return "malformed tree";
+        case QS_E_REFERENCE: return "unusable reference tree";
+        case QS_E_MEMORY: return "Insufficient memory!";
+        case QS_E_UNSUPPORTED: return "unsupported input";
+        case QS_E_STATE: return "call order";
+        default: return "unknown error";
+    }
+}
+
+const char* qs_last_error(const qs_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int qs_create(qs_ctx** out, int n_taxa, int cint_bytes, int mode, int device, int shard_index, int shard_count) {
+    if (!out) return QS_E_ARG;
+    *out = nullptr;
+    if (n_taxa < 4 || n_taxa > 32768) return QS_E_ARG;
+    if (cint_bytes != 1 && cint_bytes != 2 && cint_bytes != 4 && cint_bytes != 8) return QS_E_ARG;
+    if (mode != QS_MODE_TABLE && mode != QS_MODE_TABLE_FREE) return QS_E_ARG;
+    if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return QS_E_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return QS_E_CUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) return QS_E_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return QS_E_CUDA;
+    if (prop.major < 10) return QS_E_CUDA;   // sm_100a code only
+    qs_ctx* c = new qs_ctx();
+    c->device = device; c->n = n_taxa; c->n_pad = (n_taxa + 7) / 8 * 8; c->cint_bytes = cint_bytes; c->mode = mode;
+    c->shard_index = shard_index; c->shard_count = shard_count;
+    c->num_sms = prop.multiProcessorCount; c->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    shard_bounds(n_taxa, shard_index, shard_count, &c->d_begin, &c->d_end);
+    c->rank_begin = binom4((uint64_t)c->d_begin); c->rank_end = binom4((uint64_t)c->d_end);
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return QS_E_CUDA; }
+    c->stream = c->own_stream;
+    for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { free_all(c); delete c; return QS_E_CUDA; }
+    if (cudaMalloc((void**)&c->d_flags, 2 * sizeof(int)) != cudaSuccess) { free_all(c); delete c; return QS_E_CUDA; }
+    *out = c;
+    return QS_OK;
+}
+
+int qs_destroy(qs_ctx* ctx) {
+    if (!ctx) return QS_E_ARG;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    free_all(ctx);
+    delete ctx;
+    return QS_OK;
+}
+
+int qs_set_stream(qs_ctx* ctx, void* cuda_stream) {
+    if (!ctx) return QS_E_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return QS_OK;
+}
+
+int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int32_t* parent_edge, const int32_t* leaf_lookup_id,
+                     const int32_t* first_child, const int32_t* next_sibling) {
+    if (!ctx || !parent || !parent_edge || !leaf_lookup_id || !first_child || !next_sibling) return QS_E_ARG;
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    ctx->has_ref = false;
+    int r = build_reference(ctx, n_nodes, parent, parent_edge, leaf_lookup_id, first_child, next_sibling);
+    if (r) return r;
+    const size_t n = ctx->n;
+    if ((r = dev_alloc(ctx, &ctx->d_lca, n * n))) return r;
+    if ((r = dev_alloc(ctx, &ctx->d_idepth, (size_t)ctx->ref.n_inner))) return r;
+    QS_CUDA(ctx, cudaMemcpy(ctx->d_lca, ctx->ref.lca.data(), n * n * 2, cudaMemcpyHostToDevice));
+    QS_CUDA(ctx, cudaMemcpy(ctx->d_idepth, ctx->ref.idepth.data(), (size_t)ctx->ref.n_inner * 2, cudaMemcpyHostToDevice));
+    if (ctx->d_pair_sums) { cudaFree(ctx->d_pair_sums); ctx->d_pair_sums = nullptr; }
+    if (ctx->d_pair_best) { cudaFree(ctx->d_pair_best); ctx->d_pair_best = nullptr; }
+    ctx->fused_partials_valid = false;
+    ctx->has_ref = true;
+    return QS_OK;
+}
+
+int qs_clear_trees(qs_ctx* ctx) {
+    if (!ctx) return QS_E_ARG;
+    ctx->m = 0; ctx->total_nodes = 0; ctx->max_nodes = 0;
+    ctx->h_off.assign(1, 0);
+    ctx->counted = false; ctx->dist_valid = false; ctx->fused_partials_valid = false;
+    return QS_OK;
+}
+
+int qs_num_trees(const qs_ctx* ctx, int64_t* n_trees) {
+    if (!ctx || !n_trees) return QS_E_ARG;
+    *n_trees = ctx->m;
+    return QS_OK;
+}
+
+int qs_add_trees(qs_ctx* ctx, int n_trees, const int64_t* node_offsets, const int32_t* parent, const int32_t* leaf_lookup_id) {
+    if (!ctx || n_trees < 0 || !node_offsets || !parent || !leaf_lookup_id) return QS_E_ARG;
+    if (n_trees == 0) return QS_OK;
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (node_offsets[0] != 0) QS_FAIL(ctx, QS_E_TREE, "node_offsets[0] must be 0");
+    int mx = ctx->max_nodes;
+    for (int t = 0; t < n_trees; ++t) {
+        int64_t cnt = node_offsets[t + 1] - node_offsets[t];
+        if (cnt < 1 || cnt > 1000000) QS_FAIL(ctx, QS_E_TREE, "tree %d has %lld nodes", t, (long long)cnt);
+        if (parent[node_offsets[t]] != -1) QS_FAIL(ctx, QS_E_TREE, "tree %d: first node must be the root (parent -1)", t);
+        mx = std::max<int>(mx, (int)cnt);
+    }
+    const int64_t add_nodes = node_offsets[n_trees];
+    const int64_t new_m = ctx->m + n_trees, new_nodes = ctx->total_nodes + add_nodes;
+    if (new_m > 0x7fffffffLL) QS_FAIL(ctx, QS_E_UNSUPPORTED, "too many trees");
+    // grow device arrays (amortised doubling), preserving earlier trees
+    if (new_nodes > ctx->cap_nodes) {
+        int64_t cap = std::max<int64_t>(new_nodes, ctx->cap_nodes * 2);
+        int32_t *np = nullptr, *nl = nullptr;
+        if (cudaMalloc((void**)&np, cap * 4) != cudaSuccess || cudaMalloc((void**)&nl, cap * 4) != cudaSuccess) {
+            cudaGetLastError(); cudaFree(np);
+            QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! (tree arrays)");
+        }
+        if (ctx->total_nodes) {
+            QS_CUDA(ctx, cudaMemcpyAsync(np, ctx->d_parent, ctx->total_nodes * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            QS_CUDA(ctx, cudaMemcpyAsync(nl, ctx->d_leaf, ctx->total_nodes * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        cudaFree(ctx->d_parent); cudaFree(ctx->d_leaf);
+        ctx->d_parent = np; ctx->d_leaf = nl; ctx->cap_nodes = cap;
+    }
+    if (new_m + 1 > ctx->cap_trees) {
+        int64_t cap = std::max<int64_t>(new_m + 1, ctx->cap_trees * 2);
+        int64_t* no = nullptr;
+        if (cudaMalloc((void**)&no, cap * 8) != cudaSuccess) { cudaGetLastError(); QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! (tree offsets)"); }
+        cudaFree(ctx->d_off);
+        ctx->d_off = no; ctx->cap_trees = cap;
+        if (ctx->m) QS_CUDA(ctx, cudaMemcpyAsync(ctx->d_off, ctx->h_off.data(), (ctx->m + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int64_t base = ctx->total_nodes;
+    ctx->h_off.reserve(new_m + 1);
+    for (int t = 1; t <= n_trees; ++t) ctx->h_off.push_back(base + node_offsets[t]);
+    QS_CUDA(ctx, cudaMemcpyAsync(ctx->d_parent + base, parent, add_nodes * 4, cudaMemcpyHostToDevice, ctx->stream));
+    QS_CUDA(ctx, cudaMemcpyAsync(ctx->d_leaf + base, leaf_lookup_id, add_nodes * 4, cudaMemcpyHostToDevice, ctx->stream));
+    QS_CUDA(ctx, cudaMemcpyAsync(ctx->d_off + ctx->m, ctx->h_off.data() + ctx->m, (n_trees + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+    QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // caller may reuse its buffers
+    ctx->m = new_m; ctx->total_nodes = new_nodes; ctx->max_nodes = mx;
+    ctx->counted = false; ctx->dist_valid = false; ctx->fused_partials_valid = false;
+    return QS_OK;
+}
+
+int qs_count(qs_ctx* ctx) {
+    if (!ctx) return QS_E_ARG;
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (ctx->m == 0) QS_FAIL(ctx, QS_E_STATE, "no evaluation trees were added");
+    if ((uint64_t)ctx->m > cint_mask(ctx->cint_bytes)) QS_FAIL(ctx, QS_E_ARG, "%lld trees do not fit a %d-byte counter", (long long)ctx->m, ctx->cint_bytes);
+    ctx->counted = false; ctx->fused_partials_valid = false;
+    int r;
+    QS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    if ((r = run_distances(ctx))) return r;
+    QS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    const uint64_t nq = ctx->rank_end - ctx->rank_begin;
+    if (ctx->mode == QS_MODE_TABLE) {
+        if (ctx->table_elems != nq * 3 || !ctx->d_table) {
+            if (ctx->d_table) { cudaFree(ctx->d_table); ctx->d_table = nullptr; }
+            if (nq) {
+                cudaError_t e = cudaMalloc(&ctx->d_table, (size_t)nq * 3 * ctx->cint_bytes);
+                if (e != cudaSuccess) { cudaGetLastError(); QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! count table of %llu bytes does not fit this device", (unsigned long long)(nq * 3 * ctx->cint_bytes)); }
+            }
+            ctx->table_elems = nq * 3;
+        }
+    }
+    QS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    if (nq) {
+        if (ctx->mode == QS_MODE_TABLE && small_path_ok(ctx)) r = run_count_small(ctx);
+        else r = run_count_tiled(ctx);
+        if (r) return r;
+    }
+    QS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
+    int flags[2] = {0, 0};
+    QS_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->dist_ms = ms;
+    cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->count_ms = ms;
+    if (flags[1] != 0) QS_FAIL(ctx, QS_E_TREE, "malformed evaluation tree (code %d): need parent[i] < i, leaf ids in [0,n) exactly on leaves, each taxon at most once per tree", flags[1]);
+    if (flags[0] > kMaxHalfExact) QS_FAIL(ctx, QS_E_UNSUPPORTED, "an evaluation tree has a leaf-to-leaf path of %d edges; this build packs distances in fp16 (exact up to %d)", flags[0], kMaxHalfExact);
+    ctx->counted = true;
+    return QS_OK;
+}
+
+int qs_score_num_pairs(const qs_ctx* ctx, int64_t* n_pairs) {
+    if (!ctx || !n_pairs) return QS_E_ARG;
+    *n_pairs = (int64_t)ctx->ref.n_inner * ctx->ref.n_inner;
+    return QS_OK;
+}
+
+int qs_score_partials(qs_ctx* ctx, int count_scale, double* lqic_partial, uint64_t* pair_sums) {
+    if (!ctx || !lqic_partial || !pair_sums) return QS_E_ARG;
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int r = run_score_scan(ctx, count_scale);
+    if (r) return r;
+    lqic_from_pairs(ctx, lqic_partial);
+    memcpy(pair_sums, ctx->h_pair_sums.data(), ctx->h_pair_sums.size() * 8);
+    return QS_OK;
+}
+
+int qs_score_finalize(qs_ctx* ctx, int exact_qp, const double* lqic_reduced, const uint64_t* pair_sums_reduced,
+                      double* lqic, double* qpic, double* eqpic) {
+    if (!ctx || !lqic_reduced || !pair_sums_reduced || !lqic) return QS_E_ARG;
+    if (!ctx->has_ref) QS_FAIL(ctx, QS_E_STATE, "qs_set_reference has not been called");
+    const int E = ctx->ref.n_nodes - 1;
+    if (lqic != lqic_reduced) memcpy(lqic, lqic_reduced, (size_t)E * 8);
+    qp_from_pairs(ctx, pair_sums_reduced, exact_qp, qpic, eqpic);
+    return QS_OK;
+}
+
+int qs_score(qs_ctx* ctx, int count_scale, int exact_qp, double* lqic, double* qpic, double* eqpic) {
+    if (!ctx || !lqic) return QS_E_ARG;
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int r = run_score_scan(ctx, count_scale);
+    if (r) return r;
+    lqic_from_pairs(ctx, lqic);
+    qp_from_pairs(ctx, (const uint64_t*)ctx->h_pair_sums.data(), exact_qp, qpic, eqpic);
+    return QS_OK;
+}
+
+int qs_shard_range(const qs_ctx* ctx, uint64_t* rank_begin, uint64_t* rank_end) {
+    if (!ctx || !rank_begin || !rank_end) return QS_E_ARG;
+    *rank_begin = ctx->rank_begin; *rank_end = ctx->rank_end;
+    return QS_OK;
+}
+
+int qs_get_counts(qs_ctx* ctx, uint64_t rank_begin, uint64_t rank_end, void* out) {
+    if (!ctx || !out || rank_end < rank_begin) return QS_E_ARG;
+    if (ctx->mode != QS_MODE_TABLE) QS_FAIL(ctx, QS_E_STATE, "table-free context keeps no table");
+    if (!ctx->counted) QS_FAIL(ctx, QS_E_STATE, "qs_count has not been called");
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t eb = 3 * (size_t)ctx->cint_bytes;
+    memset(out, 0, (rank_end - rank_begin) * eb);
+    const uint64_t lo = std::max(rank_begin, ctx->rank_begin), hi = std::min(rank_end, ctx->rank_end);
+    if (lo < hi) {
+        QS_CUDA(ctx, cudaMemcpyAsync((char*)out + (lo - rank_begin) * eb, (const char*)ctx->d_table + (lo - ctx->rank_begin) * eb, (hi - lo) * eb,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    return QS_OK;
+}
+
+int qs_get_distances(qs_ctx* ctx, int64_t tree, uint16_t* out) {
+    if (!ctx || !out) return QS_E_ARG;
+    if (!ctx->dist_valid) QS_FAIL(ctx, QS_E_STATE, "distance matrices are built by qs_count");
+    if (tree < 0 || tree >= ctx->m) return QS_E_ARG;
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    uint16_t* tmp = nullptr;
+    const int n = ctx->n;
+    QS_CUDA(ctx, cudaMalloc((void**)&tmp, (size_t)n * n * 2));
+    qs_dist_to_u16_kernel<<<(n * n + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_D + (size_t)tree * n * ctx->n_pad, n, ctx->n_pad, tmp);
+    ctx->launches++;
+    cudaError_t e = cudaMemcpyAsync(out, tmp, (size_t)n * n * 2, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    QS_CUDA(ctx, e);
+    return QS_OK;
+}
+
+int qs_write_raw_qic(qs_ctx* ctx, int count_scale, const char* const* taxon_names, const char* path) {
+    if (!ctx || !taxon_names || !path) return QS_E_ARG;
+    if (ctx->mode != QS_MODE_TABLE || ctx->shard_count != 1) QS_FAIL(ctx, QS_E_STATE, "raw QIC needs a single-shard table context");
+    if (!ctx->counted || !ctx->has_ref) QS_FAIL(ctx, QS_E_STATE, "needs qs_set_reference and qs_count");
+    if (count_scale != 1 && count_scale != 2) return QS_E_ARG;
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t nq = ctx->rank_end - ctx->rank_begin;
+    const size_t eb = (size_t)ctx->cint_bytes;
+    std::vector<unsigned char> tab((size_t)nq * 3 * eb);
+    QS_CUDA(ctx, cudaMemcpyAsync(tab.data(), ctx->d_table, tab.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    FILE* f = fopen(path, "w");
+    if (!f) QS_FAIL(ctx, QS_E_ARG, "cannot open %s for writing", path);
+    const HostRef& R = ctx->ref;
+    const int n = ctx->n;
+    const uint64_t mask = cint_mask(ctx->cint_bytes);
+    auto get = [&](uint64_t idx) -> uint64_t {
+        uint64_t v = 0;
+        memcpy(&v, tab.data() + idx * eb, eb);
+        return (v * (uint64_t)count_scale) & mask;
+    };
+    // printRawQICScores order: a outermost .. d innermost (QuartetScoreComputer.hpp:626-629)
+    for (int a = 0; a < n; ++a) for (int b = a + 1; b < n; ++b) for (int cc = b + 1; cc < n; ++cc) {
+        const int p = R.lca[(size_t)a * n + b], q = R.lca[(size_t)b * n + cc];
+        const int dp = R.idepth[p], dq = R.idepth[q];
+        for (int d = cc + 1; d < n; ++d) {
+            const int dr = R.idepth[R.lca[(size_t)cc * n + d]];
+            const int S0 = dp + dr, S2 = std::min(dp, std::min(dq, dr)) + dq;
+            if (S0 == S2) continue;                                   // unresolved in the reference tree (:559-562)
+            const uint64_t rk = (quartet_rank(a, b, cc, d) - ctx->rank_begin) * 3;
+            const uint64_t c0 = get(rk), c1 = get(rk + 1), c2 = get(rk + 2);
+            char num[64];
+            if (S0 > S2) {
+                snprintf(num, sizeof(num), "%g", host_log_score(c0, c1, c2));
+                fprintf(f, "(%s,%s|%s,%s): %s\n", taxon_names[a], taxon_names[b], taxon_names[cc], taxon_names[d], num);
+            } else {
+                snprintf(num, sizeof(num), "%g", host_log_score(c2, c0, c1));    // (u,z|v,w): ab|cd=uz|vw, ac|bd=uv|zw, ad|bc=uw|zv
+                fprintf(f, "(%s,%s|%s,%s): %s\n", taxon_names[a], taxon_names[d], taxon_names[b], taxon_names[cc], num);
+            }
+        }
+    }
+    fclose(f);
+    return QS_OK;
+}
+
+int qs_last_timing(const qs_ctx* ctx, double* dist_ms, double* count_ms, double* score_ms) {
+    if (!ctx) return QS_E_ARG;
+    if (dist_ms) *dist_ms = ctx->dist_ms;
+    if (count_ms) *count_ms = ctx->count_ms;
+    if (score_ms) *score_ms = ctx->score_ms;
+    return QS_OK;
+}
+
+int qs_launch_count(const qs_ctx* ctx, int64_t* n_launches) {
+    if (!ctx || !n_launches) return QS_E_ARG;
+    *n_launches = ctx->launches;
+    return QS_OK;
+}
+
+int qs_measure_alu_peak(qs_ctx* ctx, double* half2_pair_laneops_per_s, double* int32_laneops_per_s) {
+    if (!ctx) return QS_E_ARG;
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    double h = 0, i = 0;
+    cudaError_t e = ubench_alu_peak(ctx->num_sms, ctx->stream, &h, &i);
+    ctx->launches += 6;
+    QS_CUDA(ctx, e);
+    if (half2_pair_laneops_per_s) *half2_pair_laneops_per_s = h;
+    if (int32_laneops_per_s) *int32_laneops_per_s = i;
+    return QS_OK;
+}
+
+}  // extern "C"

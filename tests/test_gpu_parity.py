@@ -1,0 +1,136 @@
+"""GPU parity: the CUDA path (through the C ABI) against the reference-pinned golden fixtures and the
+CPU oracle.  Run on the B200 box with `pytest -m gpu`."""
+import os
+
+import numpy as np
+import pytest
+
+import _oracle as O
+from _cases import cint_bits_for, load_input
+from conftest import golden_cases
+from quartetscores_b200 import Context, QuartetScoreComputer
+from quartetscores_b200.newick import write_annotated_newick
+from quartetscores_b200.synth import SyntheticInput
+from quartetscores_b200.newick import flatten_reference, parse_newick
+
+pytestmark = pytest.mark.gpu
+
+
+def run_ctx(ref, flat, **kw):
+    bits = cint_bits_for(flat.n_trees)
+    ctx = Context(ref.n_taxa, bits // 8, **kw)
+    ctx.set_reference(ref)
+    ctx.add_trees(flat)
+    ctx.count()
+    return ctx
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_counts_bit_exact(name, golden):
+    g = golden(name)
+    _, ref, flat = load_input(g)
+    with run_ctx(ref, flat) as ctx:
+        got = ctx.get_counts()
+        assert got.dtype.itemsize * 8 == cint_bits_for(flat.n_trees)
+        assert np.array_equal(got.astype(np.uint32), g["counts"].astype(np.uint32))
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_distances(name, golden):
+    g = golden(name)
+    _, ref, flat = load_input(g)
+    with run_ctx(ref, flat) as ctx:
+        for t in range(min(flat.n_trees, 5)):
+            o = flat.node_offsets
+            want, _ = O.distance_matrix(flat.parent[o[t]:o[t + 1]], flat.leaf_lookup_id[o[t]:o[t + 1]], ref.n_taxa)
+            assert np.array_equal(ctx.get_distances(t), want), f"tree {t}"
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_scores_and_output_text(name, golden):
+    g = golden(name)
+    ref_root, ref, flat = load_input(g)
+    with run_ctx(ref, flat) as ctx:
+        for suffix, scale in (("", 1), ("_s", 2)):
+            lq, qp, eqp = ctx.score(scale)
+            # tolerance of the task: 1e-9 absolute per internode score; in practice identical bits
+            for got, key in ((lq, "lqic"), (qp, "qpic"), (eqp, "eqpic")):
+                want = g[key + suffix]
+                assert np.array_equal(np.isinf(got), np.isinf(want)), key + suffix
+                fin = np.isfinite(want)
+                assert np.allclose(got[fin], want[fin], rtol=0, atol=1e-9), key + suffix
+            bif = bool(np.isfinite(g["qpic"]).any())
+            text = write_annotated_newick(ref_root, ref, lq, qp if bif else None, eqp if bif else None)
+            assert text == g["out_newick" + suffix]
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_raw_qic_file(name, golden, tmp_path):
+    g = golden(name)
+    _, ref, flat = load_input(g)
+    with run_ctx(ref, flat) as ctx:
+        p = str(tmp_path / "raw.txt")
+        ctx.write_raw_qic(ref.taxa, p)
+        assert open(p).read() == g["rawqic"]
+
+
+@pytest.mark.parametrize("n,m,seed,kw", [
+    (40, 300, 11, dict(k_max=10, p_missing=0.1, p_contract=0.1)),
+    (50, 1000, 12, dict(k_max=10)),                       # BASELINE config 1 shape
+    (64, 257, 13, dict(k_max=30, nni_fraction=0.1)),
+    (9, 2500, 14, dict(k_max=3, p_missing=0.3)),           # more than one fp16 flush chunk
+    (33, 100, 15, dict(k_max=5, p_contract=0.5)),
+])
+def test_counts_vs_oracle_seeded(n, m, seed, kw):
+    s = SyntheticInput(n, m, seed, want_newick=False, **kw)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    want = O.count_clades_compact(n, s.flat) // 2           # reference enumeration (doubled table) halved
+    with run_ctx(ref, s.flat) as ctx:
+        got = ctx.get_counts().astype(np.uint32)
+    assert np.array_equal(got, want)
+
+
+def test_scores_vs_oracle_seeded():
+    s = SyntheticInput(36, 400, 21, k_max=12, p_missing=0.05, want_newick=False)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    with run_ctx(ref, s.flat) as ctx:
+        table = ctx.get_counts().astype(np.uint32)
+        lq, qp, eqp = ctx.score(1)
+    wl, wq, we, bif = O.score(ref, table, 1, 16)
+    assert bif
+    for got, want in ((lq, wl), (qp, wq), (eqp, we)):
+        assert np.array_equal(np.isinf(got), np.isinf(want))
+        fin = np.isfinite(want)
+        assert np.allclose(got[fin], want[fin], rtol=0, atol=1e-9)
+
+
+def test_mirror_class_known_answer(golden):
+    g = golden("c1_known_answer")
+    qsc = QuartetScoreComputer(g["ref_newick"], g["eval_newick"])
+    text = write_annotated_newick(qsc.ref_root, qsc.ref, qsc.getLQICScores(), qsc.getQPICScores(), qsc.getEQPICScores())
+    assert text == g["out_newick"]
+    # ABCD 2 1 0, and any argument order gives the matching pairing
+    assert qsc.countQuartetOccurrences(0, 1, 2, 3) == (2, 1, 0)
+    assert qsc.countQuartetOccurrences(0, 2, 1, 3) == (1, 2, 0)
+    assert qsc.countQuartetOccurrences(3, 0, 2, 1) == (0, 2, 1)   # 30|21 = slot 2, 32|01 = slot 0, 31|02 = slot 1
+
+
+def test_unknown_taxon_rejected(golden):
+    g = golden("c1_known_answer")
+    with pytest.raises(IndexError):
+        QuartetScoreComputer(g["ref_newick"], "((A,B),(C,Z));")
+
+
+def test_bad_tree_encoding_rejected(golden):
+    g = golden("c1_known_answer")
+    _, ref, flat = load_input(g)
+    from quartetscores_b200 import QSError
+    bad = flat.leaf_lookup_id.copy()
+    leaves = np.nonzero(bad >= 0)[0]
+    bad[leaves[1]] = bad[leaves[0]]          # duplicate taxon inside the first tree
+    ctx = Context(ref.n_taxa, 1)
+    ctx.set_reference(ref)
+    ctx.add_trees_raw(flat.node_offsets, flat.parent, bad)
+    with pytest.raises(QSError):
+        ctx.count()
+    ctx.close()
