@@ -279,7 +279,9 @@ int run_count_small(qs_ctx* c) {
     size_t smem = 128 + (size_t)CS_STAGES * tps * a.tree_bytes;
     QS_CUDA(c, cudaFuncSetAttribute(qs_count_small_kernel<kSmallThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = std::min(a.n_item_blocks * a.n_tree_chunks, c->num_sms);
+    QS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));       // count_ms brackets the counting kernel alone
     qs_count_small_kernel<kSmallThreads><<<grid, kSmallThreads, smem, c->stream>>>(a);
+    QS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     c->launches++;
     QS_CUDA(c, cudaGetLastError());
     // workspace -> CINT table
@@ -679,12 +681,12 @@ int qs_count(qs_ctx* ctx) {
         }
     }
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
+    QS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     if (nq) {
         if (ctx->mode == QS_MODE_TABLE && small_path_ok(ctx)) r = run_count_small(ctx);
         else r = run_count_tiled(ctx);
         if (r) return r;
     }
-    QS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     int flags[2] = {0, 0};
     QS_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
     QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
