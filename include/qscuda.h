@@ -65,6 +65,10 @@ int qs_abi_version(void);
  * own stream).  Lets a host framework time the kernels with its own events. */
 int qs_set_stream(qs_ctx* ctx, void* cuda_stream);
 
+/* Table-free contexts score while they count, so the count semantics must be known before qs_count:
+ * 1 = runtime-efficient table (default), 2 = the reference's -s table (doubled, CINT-wrapped counts). */
+int qs_set_count_scale(qs_ctx* ctx, int count_scale);
+
 /* Replaces: the reference-tree half of the QuartetScoreComputer / QuartetCounterLookup constructors
  * (QuartetScoreComputer.hpp:710-718, QuartetCounterLookup.hpp:249-258, TreeInformation.hpp:95-113).
  * Nodes are numbered as genesis numbers them (root 0, parent[i] < i), parent_edge[i] is the genesis

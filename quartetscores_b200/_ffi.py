@@ -29,6 +29,7 @@ SIGNATURES = {
     "qs_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "qs_destroy": (C.c_int, [C.c_void_p]),
     "qs_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "qs_set_count_scale": (C.c_int, [C.c_void_p, C.c_int]),
     "qs_set_reference": (C.c_int, [C.c_void_p, C.c_int, _i32p, _i32p, _i32p, _i32p, _i32p]),
     "qs_add_trees": (C.c_int, [C.c_void_p, C.c_int, _i64p, _i32p, _i32p]),
     "qs_clear_trees": (C.c_int, [C.c_void_p]),

@@ -71,6 +71,9 @@ class Context:
     def set_stream(self, cuda_stream_handle: int):
         self._check(self._lib.qs_set_stream(self._h, C.c_void_p(cuda_stream_handle)), "qs_set_stream")
 
+    def set_count_scale(self, count_scale: int):
+        self._check(self._lib.qs_set_count_scale(self._h, count_scale), "qs_set_count_scale")
+
     def set_reference(self, ref: FlatReference):
         arrs = [np.ascontiguousarray(x, np.int32) for x in (ref.parent, ref.parent_edge, ref.leaf_lookup_id, ref.first_child, ref.next_sibling)]
         self._check(self._lib.qs_set_reference(self._h, ref.n_nodes, *[_ptr(a, C.c_int32) for a in arrs]), "qs_set_reference")

@@ -29,6 +29,7 @@
 // PX/PY/CD — so no thread is idle; only 8-aligned chunk boundaries waste lanes.
 #pragma once
 #include "common.cuh"
+#include "count_roles.cuh"
 
 namespace qs {
 
@@ -123,12 +124,8 @@ __global__ void __launch_bounds__(THREADS, 1) qs_count_small_kernel(const CountS
         const uint32_t oYba = yb * rowb + yia * 16u, oYca = yc * rowb + yia * 16u;
         const uint32_t oYbd = yb * rowb + yid * 16u, oYcd = yc * rowb + yid * 16u;
 
-        __half2 sx1[8][4], sx2[8][4], sy0[8][4];
-        const __half2 zero = __float2half2_rn(0.f);
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int p = 0; p < 4; ++p) { sx1[j][p] = zero; sx2[j][p] = zero; sy0[j][p] = zero; }
+        XCounters xc_; YCounters yc_;
+        zero(xc_); zero(yc_);
 
         // ---- stream the trees of this chunk through shared memory ------------------------------
         const int ntrees = t1 - t0;
@@ -148,39 +145,8 @@ __global__ void __launch_bounds__(THREADS, 1) qs_count_small_kernel(const CountS
             const int nt = min(a.trees_per_stage, ntrees - s * a.trees_per_stage);
             const unsigned char* base = bufs + buf * stage_bytes;
             for (int tt = 0; tt < nt; ++tt, base += a.tree_bytes) {
-                // role X: rows c and d, column chunks ia (a) and ib (b)
-                {
-                    uint4 ca = lds128(base, oXca), da = lds128(base, oXda), cb = lds128(base, oXcb), db = lds128(base, oXdb);
-                    __half2 ga[4], gb[4];
-                    ga[0] = __hsub2(as_h2(da.x), as_h2(ca.x)); ga[1] = __hsub2(as_h2(da.y), as_h2(ca.y));
-                    ga[2] = __hsub2(as_h2(da.z), as_h2(ca.z)); ga[3] = __hsub2(as_h2(da.w), as_h2(ca.w));
-                    gb[0] = __hsub2(as_h2(db.x), as_h2(cb.x)); gb[1] = __hsub2(as_h2(db.y), as_h2(cb.y));
-                    gb[2] = __hsub2(as_h2(db.z), as_h2(cb.z)); gb[3] = __hsub2(as_h2(db.w), as_h2(cb.w));
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const __half2 bj = (j & 1) ? __high2half2(gb[j >> 1]) : __low2half2(gb[j >> 1]);
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) {
-                            sx1[j][p] = __hadd2(sx1[j][p], __hgt2(ga[p], bj));
-                            sx2[j][p] = __hadd2(sx2[j][p], __hlt2(ga[p], bj));
-                        }
-                    }
-                }
-                // role Y: rows b and c, column chunks ia (a) and id (d)
-                {
-                    uint4 ba = lds128(base, oYba), ca = lds128(base, oYca), bd = lds128(base, oYbd), cd = lds128(base, oYcd);
-                    __half2 ga[4], gd[4];
-                    ga[0] = __hsub2(as_h2(ca.x), as_h2(ba.x)); ga[1] = __hsub2(as_h2(ca.y), as_h2(ba.y));
-                    ga[2] = __hsub2(as_h2(ca.z), as_h2(ba.z)); ga[3] = __hsub2(as_h2(ca.w), as_h2(ba.w));
-                    gd[0] = __hsub2(as_h2(cd.x), as_h2(bd.x)); gd[1] = __hsub2(as_h2(cd.y), as_h2(bd.y));
-                    gd[2] = __hsub2(as_h2(cd.z), as_h2(bd.z)); gd[3] = __hsub2(as_h2(cd.w), as_h2(bd.w));
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const __half2 dj = (j & 1) ? __high2half2(gd[j >> 1]) : __low2half2(gd[j >> 1]);
-#pragma unroll
-                        for (int p = 0; p < 4; ++p) sy0[j][p] = __hadd2(sy0[j][p], __hgt2(ga[p], dj));
-                    }
-                }
+                role_x_step(xc_, lds128(base, oXca), lds128(base, oXda), lds128(base, oXcb), lds128(base, oXdb));
+                role_y_step(yc_, lds128(base, oYba), lds128(base, oYca), lds128(base, oYbd), lds128(base, oYcd));
             }
             __syncthreads();   // everyone is done reading this buffer
             if (tid == 0 && s + CS_STAGES < nst) {
@@ -201,7 +167,7 @@ __global__ void __launch_bounds__(THREADS, 1) qs_count_small_kernel(const CountS
                 const uint64_t rb = rcd + (uint64_t)b * (b - 1) / 2;
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float2 v1 = __half22float2(sx1[j][p]), v2 = __half22float2(sx2[j][p]);
+                    const float2 v1 = __half22float2(xc_.s1[j][p]), v2 = __half22float2(xc_.s2[j][p]);
                     const int a0 = xia * 8 + 2 * p;
                     if (a0 < b) {
                         uint32_t* w = a.ws + (rb + a0) * 3;
@@ -225,7 +191,7 @@ __global__ void __launch_bounds__(THREADS, 1) qs_count_small_kernel(const CountS
                 const uint64_t rb = binom4((uint64_t)d) + binom3((uint64_t)yc) + (uint64_t)yb * (yb - 1) / 2 - a.rank_base;
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
-                    const float2 v0 = __half22float2(sy0[j][p]);
+                    const float2 v0 = __half22float2(yc_.s0[j][p]);
                     const int a0 = yia * 8 + 2 * p;
                     if (a0 < yb && v0.x != 0.f) atomicAdd(a.ws + (rb + a0) * 3, (uint32_t)v0.x);
                     if (a0 + 1 < yb && v0.y != 0.f) atomicAdd(a.ws + (rb + a0 + 1) * 3, (uint32_t)v0.y);

@@ -6,9 +6,11 @@
 // per-quartet QIC selection happens in the CUDA kernels under kernels/.
 #include "../../include/qscuda.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -84,7 +86,13 @@ struct qs_ctx {
     unsigned long long* d_pair_best = nullptr;
     std::vector<unsigned long long> h_pair_sums, h_pair_best;
     bool fused_partials_valid = false;   // table-free mode: partials accumulated by qs_count
-    int fused_scale = 0;
+    int fused_scale = 1;
+
+    // tiled counting kernel
+    ushort4* d_tiles = nullptr;
+    int n_tiles = -1;
+    uint32_t* d_scratch = nullptr;
+    int scratch_ctas = 0;
 };
 
 namespace {
@@ -150,7 +158,7 @@ void free_all(qs_ctx* c) {
     cudaFree(c->d_off); cudaFree(c->d_parent); cudaFree(c->d_leaf);
     cudaFree(c->d_D); cudaFree(c->d_flags); cudaFree(c->d_ws); cudaFree(c->d_table);
     cudaFree(c->d_PX); cudaFree(c->d_PY); cudaFree(c->d_CD);
-    cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best);
+    cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best); cudaFree(c->d_tiles); cudaFree(c->d_scratch);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
 }
@@ -296,8 +304,94 @@ int run_count_small(qs_ctx* c) {
     return QS_OK;
 }
 
+// ---- tiled counting kernel (kernels/count_tiled.cuh) ---------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_dist_tensor_map(qs_ctx* c, CUtensorMap* tm, int box_rows, int box_cols) {
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        QS_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) QS_FAIL(c, QS_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+        encode = (PFN_encodeTiled)fn;
+    }
+    const cuuint64_t gdim[3] = {(cuuint64_t)c->n_pad, (cuuint64_t)c->n, (cuuint64_t)c->m};
+    const cuuint64_t gstride[2] = {(cuuint64_t)c->n_pad * 2, (cuuint64_t)c->n * c->n_pad * 2};
+    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)c->d_D, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) QS_FAIL(c, QS_E_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
+    return QS_OK;
+}
+
+int build_tiles(qs_ctx* c) {
+    std::vector<ushort4> tiles;
+    const int dlo = std::max(3, c->d_begin), dhi = c->d_end;       // d in [dlo, dhi)
+    for (int jd = dlo / 8; jd * 8 < dhi; ++jd) {
+        const int d_max = std::min(jd * 8 + 7, dhi - 1);
+        if (d_max < dlo) continue;
+        for (int ic = 0; ic * 16 <= d_max - 1; ++ic) {
+            const int c_max = std::min(ic * 16 + 15, d_max - 1);
+            if (c_max < 2) continue;
+            for (int ib = 0; ib * 16 <= c_max - 1; ++ib) {
+                const int b_max = std::min(ib * 16 + 15, c_max - 1);
+                if (b_max < 1) continue;
+                for (int ia = 0; ia * 16 <= b_max - 1; ++ia) tiles.push_back(make_ushort4((unsigned short)ia, (unsigned short)ib, (unsigned short)ic, (unsigned short)jd));
+            }
+        }
+    }
+    if (tiles.size() > 0x7fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "too many tiles");
+    c->n_tiles = (int)tiles.size();
+    int r;
+    if ((r = dev_alloc(c, &c->d_tiles, tiles.size()))) return r;
+    if (!tiles.empty()) QS_CUDA(c, cudaMemcpy(c->d_tiles, tiles.data(), tiles.size() * sizeof(ushort4), cudaMemcpyHostToDevice));
+    return QS_OK;
+}
+
+int ensure_pair_arrays(qs_ctx* c);
+
 int run_count_tiled(qs_ctx* c) {
-    QS_FAIL(c, QS_E_UNSUPPORTED, "n = %d taxa needs the tiled counting kernel, which this build does not have yet", c->n);
+    int r;
+    if (c->n_tiles < 0 && (r = build_tiles(c))) return r;
+    if (c->n_tiles == 0) return QS_OK;
+    const int grid = std::min(c->n_tiles, c->num_sms);
+    if (c->scratch_ctas < grid) {
+        if ((r = dev_alloc(c, &c->d_scratch, (size_t)grid * CT_TILE_Q * 3))) { c->scratch_ctas = 0; return r; }
+        c->scratch_ctas = grid;
+    }
+    CUtensorMap tm16x16, tm8x16, tm16x8;
+    if ((r = make_dist_tensor_map(c, &tm16x16, 16, 16))) return r;
+    if ((r = make_dist_tensor_map(c, &tm8x16, 8, 16))) return r;
+    if ((r = make_dist_tensor_map(c, &tm16x8, 16, 8))) return r;
+    CountTiledArgs a;
+    memset(&a, 0, sizeof(a));
+    a.tiles = c->d_tiles; a.n_tiles = c->n_tiles; a.n = c->n; a.m = (int)c->m; a.d_begin = c->d_begin; a.d_end = c->d_end;
+    a.rank_base = c->rank_begin; a.scratch = c->d_scratch; a.cint_bytes = c->cint_bytes;
+    a.table = (c->mode == QS_MODE_TABLE) ? c->d_table : nullptr;
+    a.fused_score = (c->mode == QS_MODE_TABLE_FREE) ? 1 : 0;
+    if (a.fused_score) {
+        if (!c->has_ref) QS_FAIL(c, QS_E_STATE, "a table-free context scores while it counts: call qs_set_reference before qs_count");
+        if ((r = ensure_pair_arrays(c))) return r;
+        const size_t I = c->ref.n_inner;
+        QS_CUDA(c, cudaMemsetAsync(c->d_pair_sums, 0, I * I * 3 * 8, c->stream));
+        QS_CUDA(c, cudaMemsetAsync(c->d_pair_best, 0xFF, I * I * 8, c->stream));
+        ScoreArgs& sa = a.sa;
+        sa.table = nullptr; sa.rank_base = c->rank_begin; sa.lca = c->d_lca; sa.idepth = c->d_idepth; sa.pair_sums = c->d_pair_sums;
+        sa.pair_best = c->d_pair_best; sa.PB = nullptr; sa.n = c->n; sa.I = (int)I; sa.d_begin = c->d_begin; sa.d_end = c->d_end;
+        sa.count_scale = c->fused_scale; sa.cint_mask = cint_mask(c->cint_bytes); sa.bifurcating = c->ref.bifurcating ? 1 : 0;
+    }
+    const size_t smem = 128 + (size_t)CT_STAGES * CT_TPS * CT_TREE_BYTES;
+    QS_CUDA(c, cudaFuncSetAttribute(qs_count_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    QS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
+    qs_count_tiled_kernel<<<grid, CT_THREADS, smem, c->stream>>>(a, tm16x16, tm8x16, tm16x8);
+    QS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    c->launches++;
+    QS_CUDA(c, cudaGetLastError());
+    if (a.fused_score) c->fused_partials_valid = true;
+    return QS_OK;
 }
 
 int build_reference(qs_ctx* c, int n_nodes, const int32_t* parent, const int32_t* parent_edge, const int32_t* leaf_id,
@@ -569,6 +663,12 @@ int qs_destroy(qs_ctx* ctx) {
     return QS_OK;
 }
 
+int qs_set_count_scale(qs_ctx* ctx, int count_scale) {
+    if (!ctx || (count_scale != 1 && count_scale != 2)) return QS_E_ARG;
+    ctx->fused_scale = count_scale;
+    return QS_OK;
+}
+
 int qs_set_stream(qs_ctx* ctx, void* cuda_stream) {
     if (!ctx) return QS_E_ARG;
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
@@ -683,7 +783,8 @@ int qs_count(qs_ctx* ctx) {
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     if (nq) {
-        if (ctx->mode == QS_MODE_TABLE && small_path_ok(ctx)) r = run_count_small(ctx);
+        const char* force = getenv("QS_FORCE_TILED");      // test hook: exercise the tiled kernel on small inputs
+        if (ctx->mode == QS_MODE_TABLE && small_path_ok(ctx) && !(force && force[0] == '1')) r = run_count_small(ctx);
         else r = run_count_tiled(ctx);
         if (r) return r;
     }

@@ -134,3 +134,56 @@ def test_bad_tree_encoding_rejected(golden):
     with pytest.raises(QSError):
         ctx.count()
     ctx.close()
+
+
+# ---- tiled kernel (large-n path) and table-free mode, forced on small inputs -----------------------
+
+@pytest.fixture
+def force_tiled(monkeypatch):
+    monkeypatch.setenv("QS_FORCE_TILED", "1")
+
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_tiled_kernel_golden(name, golden, force_tiled):
+    g = golden(name)
+    ref_root, ref, flat = load_input(g)
+    with run_ctx(ref, flat) as ctx:
+        assert np.array_equal(ctx.get_counts().astype(np.uint32), g["counts"].astype(np.uint32))
+        lq, qp, eqp = ctx.score(1)
+        bif = bool(np.isfinite(g["qpic"]).any())
+        assert write_annotated_newick(ref_root, ref, lq, qp if bif else None, eqp if bif else None) == g["out_newick"]
+
+
+@pytest.mark.parametrize("n,m,seed,kw", [
+    (40, 300, 31, dict(k_max=10, p_missing=0.1, p_contract=0.1)),
+    (70, 120, 32, dict(k_max=15)),
+    (19, 2300, 33, dict(k_max=4, p_missing=0.2)),          # > 2048 trees: in-kernel fp16 flush
+])
+def test_tiled_kernel_vs_oracle(n, m, seed, kw, force_tiled):
+    s = SyntheticInput(n, m, seed, want_newick=False, **kw)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    want = O.count_clades_compact(n, s.flat) // 2
+    with run_ctx(ref, s.flat) as ctx:
+        assert np.array_equal(ctx.get_counts().astype(np.uint32), want)
+
+
+@pytest.mark.parametrize("name", golden_cases())
+@pytest.mark.parametrize("scale,suffix", [(1, ""), (2, "_s")])
+def test_table_free_mode_golden(name, golden, scale, suffix):
+    """-s analogue: no table, quartets are scored inside the counting kernel's epilogue."""
+    from quartetscores_b200 import QS_MODE_TABLE_FREE
+    g = golden(name)
+    ref_root, ref, flat = load_input(g)
+    ctx = Context(ref.n_taxa, cint_bits_for(flat.n_trees) // 8, mode=QS_MODE_TABLE_FREE)
+    ctx.set_reference(ref)
+    ctx.set_count_scale(scale)
+    ctx.add_trees(flat)
+    ctx.count()
+    lq, qp, eqp = ctx.score(scale)
+    ctx.close()
+    bif = bool(np.isfinite(g["qpic"]).any())
+    assert write_annotated_newick(ref_root, ref, lq, qp if bif else None, eqp if bif else None) == g["out_newick" + suffix]
+    for got, key in ((lq, "lqic"), (qp, "qpic"), (eqp, "eqpic")):
+        want = g[key + suffix]
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isinf(got), np.isinf(want)) and np.allclose(got[fin], want[fin], rtol=0, atol=1e-9)
