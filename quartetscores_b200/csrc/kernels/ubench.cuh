@@ -19,10 +19,11 @@ __global__ void __launch_bounds__(512) qs_ubench_kernel(uint32_t* out, const uin
         for (int i = 0; i < NCH; ++i) {
             if (MIX == 0) {
                 uint32_t m;
-                asm volatile("set.gt.f16x2.f16x2 %0, %1, %2;" : "=r"(m) : "r"(x[i]), "r"(y));
+                // the compare reads another chain's accumulator, so ptxas cannot hoist it out of the loop
+                asm volatile("set.gt.f16x2.f16x2 %0, %1, %2;" : "=r"(m) : "r"(x[i]), "r"(acc[(i + 5) % NCH]));
                 asm volatile("add.f16x2 %0, %0, %1;" : "+r"(acc[i]) : "r"(m));
             } else {
-                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(acc[i]) : "r"(x[i]), "r"(y));
+                asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(acc[i]) : "r"(acc[(i + 5) % NCH]), "r"(y));
             }
         }
     }
