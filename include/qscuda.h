@@ -48,6 +48,12 @@ enum {
     QS_MODE_TABLE_FREE = 1  /* -s / savemem analogue: counts are scored as they are produced, no table */
 };
 
+/* device for qs_create: a host-only context.  It makes no CUDA call and supports only the host-side pieces
+ * of the multi-GPU path (qs_set_reference, qs_score_finalize, qs_score_num_pairs, qs_shard_range) — e.g. a
+ * rank that only combines reduced partials, or CPU tests of that logic.  Every compute entry point fails
+ * on it with QS_E_STATE: there is no CPU fallback. */
+#define QS_DEVICE_NONE (-1)
+
 typedef struct qs_ctx qs_ctx;
 
 /* Replaces: construction of QuartetScoreComputer<CINT> (src/QuartetScoreComputer.hpp:698-745) — CINT
@@ -120,6 +126,10 @@ int qs_score_finalize(qs_ctx* ctx, int exact_qp, const double* lqic_reduced, con
 int qs_get_counts(qs_ctx* ctx, uint64_t rank_begin, uint64_t rank_end, void* out);
 /* Rank range [begin,end) owned by this shard. */
 int qs_shard_range(const qs_ctx* ctx, uint64_t* rank_begin, uint64_t* rank_end);
+/* The sharding rule itself (pure function, no context): shard g of G owns the quartets whose largest id s3
+ * lies in [s3_begin, s3_end), boundaries ~ n*(g/G)^(1/4) rounded to 8, i.e. the rank range
+ * [C(s3_begin,4), C(s3_end,4)).  Output pointers may be NULL. */
+int qs_shard_bounds(int n_taxa, int shard_index, int shard_count, int* s3_begin, int* s3_end, uint64_t* rank_begin, uint64_t* rank_end);
 
 /* Parity hook for the distance kernel: tree t's matrix as n x n uint16 (0xFFFF = taxon missing). */
 int qs_get_distances(qs_ctx* ctx, int64_t tree, uint16_t* out);
@@ -134,11 +144,16 @@ int qs_write_raw_qic(qs_ctx* ctx, int count_scale, const char* const* taxon_name
 int qs_last_timing(const qs_ctx* ctx, double* dist_ms, double* count_ms, double* score_ms);
 int qs_launch_count(const qs_ctx* ctx, int64_t* n_launches);
 
-/* Live micro-benchmark of the issue rate the counting kernel is bound by: packed fp16x2
- * compare (HSET2) + accumulate (HADD2) lane-operations per second on this device, and the plain
- * int32 IADD3/LOP3 rate, both measured with the clocks the device sustains right now.  Used as the
- * roofline denominator in bench.py. */
-int qs_measure_alu_peak(qs_ctx* ctx, double* half2_pair_laneops_per_s, double* int32_laneops_per_s);
+/* Tree classes found by the last qs_count: class A = gene trees that contain all n taxa and have no node of
+ * degree > 3, so they resolve every quartet and need two compares per quartet instead of three
+ * (kernels/count_items.cuh).  Reported so that bench.py can state the algorithmic work of a run. */
+int qs_tree_classes(const qs_ctx* ctx, int64_t* n_class_a, int64_t* n_class_b);
+
+/* Live micro-benchmark of the issue rate the counting kernel is bound by: packed fp16x2 compare
+ * (HSET2 -> integer mask, two per three-input IADD3 accumulate) lane-operations per second on this
+ * device, counting the HSET2 only, and the plain int32 LOP3/IADD3 rate, both measured at the clocks
+ * the device sustains right now.  Used as the roofline denominator in bench.py. */
+int qs_measure_alu_peak(qs_ctx* ctx, double* hset2_laneops_per_s, double* int32_laneops_per_s);
 
 #ifdef __cplusplus
 }

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libqscuda.so")
 QS_OK = 0
 QS_MODE_TABLE = 0
 QS_MODE_TABLE_FREE = 1
+QS_DEVICE_NONE = -1
 
 _i32p = C.POINTER(C.c_int32)
 _i64p = C.POINTER(C.c_int64)
@@ -41,10 +42,12 @@ SIGNATURES = {
     "qs_score_finalize": (C.c_int, [C.c_void_p, C.c_int, _f64p, _u64p, _f64p, _f64p, _f64p]),
     "qs_get_counts": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "qs_shard_range": (C.c_int, [C.c_void_p, _u64p, _u64p]),
+    "qs_shard_bounds": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _u64p, _u64p]),
     "qs_get_distances": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint16)]),
     "qs_write_raw_qic": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_char_p]),
     "qs_last_timing": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p]),
     "qs_launch_count": (C.c_int, [C.c_void_p, _i64p]),
+    "qs_tree_classes": (C.c_int, [C.c_void_p, _i64p, _i64p]),
     "qs_measure_alu_peak": (C.c_int, [C.c_void_p, _f64p, _f64p]),
 }
 

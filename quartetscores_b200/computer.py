@@ -161,6 +161,12 @@ class Context:
         self._check(self._lib.qs_launch_count(self._h, C.byref(v)), "qs_launch_count")
         return v.value
 
+    def tree_classes(self):
+        """(class A, class B) gene-tree counts of the last count(): class A = complete and fully resolved."""
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._lib.qs_tree_classes(self._h, C.byref(a), C.byref(b)), "qs_tree_classes")
+        return a.value, b.value
+
     def measure_alu_peak(self):
         a, b = C.c_double(), C.c_double()
         self._check(self._lib.qs_measure_alu_peak(self._h, C.byref(a), C.byref(b)), "qs_measure_alu_peak")

@@ -24,6 +24,7 @@ struct DistArgs {
     int m, n, n_pad, max_nodes;
     __half* D;
     int* max_dist;             // [0] global max over all trees (atomicMax), [1] first tree-encoding error code
+    int32_t* tree_class;       // [m] 0 = class A: all n taxa present and no node of degree > 3 (every quartet resolved), 1 = class B
 };
 
 __global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
         const int64_t off = a.node_off[t];
         const int N = (int)(a.node_off[t + 1] - off);
         __syncthreads();
-        for (int i = threadIdx.x; i < N; i += blockDim.x) { par[i] = a.parent[off + i]; fc[i] = -1; ns[i] = -1; }
+        for (int i = threadIdx.x; i < N; i += blockDim.x) { par[i] = a.parent[off + i]; fc[i] = -1; ns[i] = -1; lh[i] = 0; }
         for (int i = threadIdx.x; i < (a.n + 31) / 32; i += blockDim.x) seen[i] = 0u;
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
             dep[0] = 0;
             for (int i = 1; i < N; ++i) { if (par[i] < 0 || par[i] >= i) { bad = 1; par[i] = 0; } }
             for (int i = 1; i < N; ++i) dep[i] = dep[par[i]] + 1;
-            for (int i = N - 1; i >= 1; --i) { int p = par[i]; ns[i] = fc[p]; fc[p] = i; }
+            int maxdeg = 0;                                   // lh[] holds child counts until the tour overwrites it
+            for (int i = N - 1; i >= 1; --i) { int p = par[i]; ns[i] = fc[p]; fc[p] = i; maxdeg = max(maxdeg, ++lh[p] + (p > 0 ? 1 : 0)); }
             int k = 0, sp = 0, cur_min = 0x7fffffff;
             if (N > 0 && fc[0] == -1) {                       // single-node tree
                 int id = a.leaf_id[off];
@@ -81,6 +83,7 @@ __global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
                 }
             }
             if (bad) { atomicCAS(a.max_dist + 1, 0, bad); k = 0; }
+            a.tree_class[t] = (!bad && k == a.n && maxdeg <= 3) ? 0 : 1;
             s_k = k;
         }
         __syncthreads();
@@ -117,6 +120,30 @@ __global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
     // block max -> global
     for (int o = 16; o > 0; o >>= 1) local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, o));
     if ((threadIdx.x & 31) == 0 && local_max > 0) atomicMax(a.max_dist, local_max);
+}
+
+// class-sorted tree order (stable partition: class-A trees first) and |A|; one CTA
+__global__ void __launch_bounds__(1024) qs_order_kernel(const int32_t* __restrict__ tree_class, int m, int32_t* __restrict__ order, int32_t* __restrict__ n_class_a) {
+    __shared__ int cntA[1024];
+    __shared__ int s_totalA;
+    const int tid = threadIdx.x;
+    const int seg = (m + 1023) / 1024;
+    const int lo = min(m, tid * seg), hi = min(m, lo + seg);
+    int ca = 0;
+    for (int t = lo; t < hi; ++t) ca += (tree_class[t] == 0);
+    cntA[tid] = ca;
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int i = 0; i < 1024; ++i) { int v = cntA[i]; cntA[i] = acc; acc += v; }
+        s_totalA = acc;
+        *n_class_a = acc;
+    }
+    __syncthreads();
+    int pa = cntA[tid], pb = s_totalA + (lo - cntA[tid]);
+    for (int t = lo; t < hi; ++t) {
+        if (tree_class[t] == 0) order[pa++] = t; else order[pb++] = t;
+    }
 }
 
 // fp16 matrix of one tree -> uint16 (0xFFFF for NaN): parity hook qs_get_distances

@@ -1,5 +1,6 @@
 // ubench.cuh — live measurement of the issue rates that bound the counting kernel (roofline denominators).
-// half2 mix: HSET2.BF (ALU pipe) + HADD2 (FMA pipe), the counting kernel's inner-loop pair.
+// compare mix: 2 x HSET2 (fp16x2 compare -> integer mask) + 1 x IADD3 (three-input add of both masks), the counting
+// kernel's inner-loop triple; the reported rate counts the HSET2 lane-ops only (the pipe the kernel is bound by).
 // int32 mix: LOP3 on the ALU pipe (the classic INT32 lane rate; IADD3 issues at the same rate).
 #pragma once
 #include "common.cuh"
@@ -18,10 +19,13 @@ __global__ void __launch_bounds__(512) qs_ubench_kernel(uint32_t* out, const uin
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
             if (MIX == 0) {
-                uint32_t m;
-                // the compare reads another chain's accumulator, so ptxas cannot hoist it out of the loop
-                asm volatile("set.gt.f16x2.f16x2 %0, %1, %2;" : "=r"(m) : "r"(x[i]), "r"(acc[(i + 5) % NCH]));
-                asm volatile("add.f16x2 %0, %0, %1;" : "+r"(acc[i]) : "r"(m));
+                // the compares read other chains' accumulators, so ptxas cannot hoist them out of the loop
+                if (i & 1) {
+                    uint32_t m0, m1;
+                    asm volatile("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(m0) : "r"(x[i]), "r"(acc[(i + 5) % NCH]));
+                    asm volatile("set.gt.u32.f16x2 %0, %1, %2;" : "=r"(m1) : "r"(x[i - 1]), "r"(acc[(i + 6) % NCH]));
+                    asm volatile("{.reg .s32 t; add.s32 t, %1, %2; sub.s32 %0, %0, t;}" : "+r"(acc[i]) : "r"(m0), "r"(m1));
+                }
             } else {
                 asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(acc[i]) : "r"(acc[(i + 5) % NCH]), "r"(y));
             }
@@ -33,7 +37,7 @@ __global__ void __launch_bounds__(512) qs_ubench_kernel(uint32_t* out, const uin
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
-inline cudaError_t ubench_alu_peak(int num_sms, cudaStream_t stream, double* half2_laneops, double* int_laneops) {
+inline cudaError_t ubench_alu_peak(int num_sms, cudaStream_t stream, double* hset2_laneops, double* int_laneops) {
     uint32_t *out = nullptr, *in = nullptr;
     cudaError_t e;
     if ((e = cudaMalloc((void**)&out, (size_t)num_sms * 512 * 4)) != cudaSuccess) return e;
@@ -57,13 +61,13 @@ inline cudaError_t ubench_alu_peak(int num_sms, cudaStream_t stream, double* hal
             if (rep > 0 && ms < best) best = ms;
         }
         if (e != cudaSuccess) break;
-        const double instr_per_thread = (double)iters * 16 * (mix == 0 ? 2 : 1);
+        const double instr_per_thread = (double)iters * 16;   // mix 0: 16 HSET2 (+ 8 IADD3, not counted) per iteration
         res[mix] = instr_per_thread * 512.0 * num_sms / (best * 1e-3);
     }
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(out); cudaFree(in);
     if (e == cudaSuccess) e = cudaGetLastError();
-    *half2_laneops = res[0]; *int_laneops = res[1];
+    *hset2_laneops = res[0]; *int_laneops = res[1];
     return e;
 }
 

@@ -19,7 +19,7 @@
 #include <vector>
 
 #include "kernels/common.cuh"
-#include "kernels/count_small.cuh"
+#include "kernels/count_items.cuh"
 #include "kernels/count_tiled.cuh"
 #include "kernels/dist.cuh"
 #include "kernels/score.cuh"
@@ -29,8 +29,8 @@ using namespace qs;
 
 namespace {
 
-constexpr int kMaxHalfExact = 2048;     // integers up to 2048 are exact in fp16
-constexpr int kSmallThreads = 512;
+constexpr int kMaxHalfExact = 2048;     // integers up to 2048 are exact in fp16 (distances; the counters are integer)
+constexpr int kItemThreads = 512;
 
 struct HostRef {
     int n_nodes = 0, n_inner = 0;
@@ -44,6 +44,7 @@ struct HostRef {
 
 struct qs_ctx {
     int device = 0, n = 0, n_pad = 0, cint_bytes = 2, mode = 0, shard_index = 0, shard_count = 1;
+    bool host_only = false;      // QS_DEVICE_NONE: reference bookkeeping + qs_score_finalize only
     int d_begin = 0, d_end = 0, num_sms = 148, smem_optin = 0;
     uint64_t rank_begin = 0, rank_end = 0;
     std::string err;
@@ -73,12 +74,24 @@ struct qs_ctx {
     int* d_flags = nullptr;      // [0] max distance, [1] tree error
     bool dist_valid = false;
 
+    // tree classes (kernels/dist.cuh): class A = complete and fully resolved
+    int32_t* d_class = nullptr;
+    int32_t* d_order = nullptr;
+    int32_t* d_nA = nullptr;
+    int64_t class_cap = 0, n_class_a = 0;
+    int* d_counter = nullptr;    // dynamic task / tile scheduling
+
     // counting
     uint32_t* d_ws = nullptr;
     void* d_table = nullptr;
     size_t table_elems = 0;
-    int32_t *d_PX = nullptr, *d_PY = nullptr, *d_CD = nullptr;
-    int NX = 0, NY = 0;
+    CountItem* d_items[3] = {nullptr, nullptr, nullptr};
+    int64_t n_items[3] = {0, 0, 0};
+    bool items_built = false;
+    CountTask* d_tasks = nullptr;
+    int n_tasks = 0;
+    int64_t tasks_for_m = -1;
+    __half* d_nan_tree = nullptr;
     bool counted = false;
 
     // scoring
@@ -123,14 +136,20 @@ int dev_alloc(qs_ctx* c, T** p, size_t count) {
     return QS_OK;
 }
 
-// balanced split of the rank space by the outer index d: boundaries ~ n * (g/G)^(1/4), rounded to 8
+// balanced split of the rank space by the outer index d: boundary i = the d whose C(d,4) is closest to i/G of C(n,4)
+// (~ n * (i/G)^(1/4)); no alignment is required (the tiled kernel anchors its d-tiles at the shard's first d)
 void shard_bounds(int n, int g, int G, int* d_begin, int* d_end) {
     auto bound = [&](int i) -> int {
         if (i <= 0) return 3;
         if (i >= G) return n;
-        double x = (double)n * pow((double)i / G, 0.25);
-        int v = ((int)(x + 4.0) / 8) * 8;
-        return std::min(n, std::max(3, v));
+        const long double target = (long double)binom4((uint64_t)n) * i / G;
+        int d = (int)((double)n * pow((double)i / G, 0.25));
+        d = std::min(n, std::max(3, d));
+        while (d < n && (long double)binom4((uint64_t)d) < target) ++d;
+        while (d > 3 && (long double)binom4((uint64_t)d - 1) >= target) --d;
+        // d is the smallest value with C(d,4) >= target; take d-1 if it is closer
+        if (d > 3 && target - (long double)binom4((uint64_t)d - 1) < (long double)binom4((uint64_t)d) - target) --d;
+        return std::min(n, std::max(3, d));
     };
     *d_begin = bound(g);
     *d_end = bound(g + 1);
@@ -157,63 +176,78 @@ void free_all(qs_ctx* c) {
     cudaFree(c->d_lca); cudaFree(c->d_idepth); cudaFree(c->d_PB);
     cudaFree(c->d_off); cudaFree(c->d_parent); cudaFree(c->d_leaf);
     cudaFree(c->d_D); cudaFree(c->d_flags); cudaFree(c->d_ws); cudaFree(c->d_table);
-    cudaFree(c->d_PX); cudaFree(c->d_PY); cudaFree(c->d_CD);
+    cudaFree(c->d_class); cudaFree(c->d_order); cudaFree(c->d_nA); cudaFree(c->d_counter);
+    for (auto& p : c->d_items) cudaFree(p);
+    cudaFree(c->d_tasks); cudaFree(c->d_nan_tree);
     cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best); cudaFree(c->d_tiles); cudaFree(c->d_scratch);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
 }
 
-// does the whole-matrix kernel apply?  two stages of at least one tree each must fit in shared memory
+// does the whole-matrix kernel apply?  two pipeline stages of one tree pair each must fit in shared memory
 bool small_path_ok(const qs_ctx* c) {
     size_t tree_bytes = (size_t)c->n * c->n_pad * 2;
-    return 128 + 2 * tree_bytes <= (size_t)c->smem_optin;
+    return 256 + 4 * tree_bytes <= (size_t)c->smem_optin;
 }
 
-// ---- item enumeration tables of the whole-matrix counting kernel (see kernels/count_small.cuh) -----
-int build_small_tables(qs_ctx* c) {
-    const int n = c->n;
-    std::vector<int32_t> PX(n + 1, 0), PY(n + 1, 0), CD(n + 1, 0);
-    int64_t acc = 0;
-    for (int cc = 0; cc < n; ++cc) {
-        PX[cc] = (int32_t)acc;
-        if (cc >= 2) {
-            int dlo = std::max(cc + 1, c->d_begin);
-            int64_t nd = std::max(0, c->d_end - dlo);
-            int64_t nb = (cc + 7) / 8;
-            acc += nb * (nb + 1) / 2 * nd;
+// ---- work items of the whole-matrix counting kernel (see kernels/count_items.cuh) ------------------
+int build_items(qs_ctx* c) {
+    const int n = c->n, dB = c->d_begin, dE = c->d_end;
+    std::vector<CountItem> xo, xd, y;
+    for (int cc = 2; cc < n - 1; ++cc) {
+        const int nb = (cc + 7) / 8;                       // blocks holding some b < c
+        for (int d = std::max(cc + 1, dB); d < dE; ++d) {
+            for (int ib = 0; ib < nb; ++ib) {
+                for (int ia = 0; ia < ib; ++ia) xo.push_back(CountItem{(uint16_t)cc, (uint16_t)d, (uint16_t)ia, (uint16_t)ib});
+                if (ib * 8 + 1 < cc) xd.push_back(CountItem{(uint16_t)cc, (uint16_t)d, (uint16_t)ib, (uint16_t)ib});
+            }
         }
     }
-    PX[n] = (int32_t)acc;
-    if (acc > 0x7fffffff) QS_FAIL(c, QS_E_UNSUPPORTED, "item count overflow");
-    c->NX = (int)acc;
-    acc = 0;
-    for (int cc = 0; cc < n; ++cc) {
-        CD[cc] = (int32_t)acc;
-        if (cc >= 2) {
-            int dlo = std::max(cc + 1, c->d_begin);
-            if (dlo < c->d_end) acc += (c->d_end - 1) / 8 - dlo / 8 + 1;
+    for (int b = 1; b < n - 2; ++b) {
+        const int na = (b + 7) / 8;
+        for (int cc = b + 1; cc < n - 1; ++cc) {
+            const int dlo = std::max(cc + 1, dB);
+            if (dlo >= dE) continue;
+            for (int id = dlo / 8; id <= (dE - 1) / 8; ++id)
+                for (int ia = 0; ia < na; ++ia) y.push_back(CountItem{(uint16_t)b, (uint16_t)cc, (uint16_t)ia, (uint16_t)id});
         }
     }
-    CD[n] = (int32_t)acc;
-    acc = 0;
-    for (int b = 0; b < n; ++b) {
-        PY[b] = (int32_t)acc;
-        if (b >= 1 && b + 1 < n) {
-            int64_t na = (b + 7) / 8;
-            int64_t chunks = CD[n] - CD[b + 1];
-            acc += na * chunks;
-        }
+    const std::vector<CountItem>* lists[3] = {&xo, &xd, &y};
+    for (int k = 0; k < 3; ++k) {
+        if (lists[k]->size() > 0x7fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "item count overflow");
+        c->n_items[k] = (int64_t)lists[k]->size();
+        int r;
+        if ((r = dev_alloc(c, &c->d_items[k], lists[k]->size()))) return r;
+        if (!lists[k]->empty()) QS_CUDA(c, cudaMemcpy(c->d_items[k], lists[k]->data(), lists[k]->size() * sizeof(CountItem), cudaMemcpyHostToDevice));
     }
-    PY[n] = (int32_t)acc;
-    if (acc > 0x7fffffff) QS_FAIL(c, QS_E_UNSUPPORTED, "item count overflow");
-    c->NY = (int)acc;
+    c->items_built = true;
+    return QS_OK;
+}
+
+// tasks = (kind, block of thread-items, tree class, chunk of that class); the class sizes are only known
+// on the device, so every class gets the same number of chunks and empty tasks return at once
+int build_tasks(qs_ctx* c) {
+    const int per_task[3] = {kItemThreads, 2 * kItemThreads, 2 * kItemThreads};
+    int64_t blocks[3], total_blocks = 0;
+    for (int k = 0; k < 3; ++k) { blocks[k] = (c->n_items[k] + per_task[k] - 1) / per_task[k]; total_blocks += blocks[k]; }
+    int nchunks = (int)((c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES);
+    // enough tasks for the dynamic scheduler to balance (~8 per SM), but chunks of at least 256 trees
+    while ((int64_t)nchunks * total_blocks < 8LL * c->num_sms && c->m / (nchunks + 1) >= 256) ++nchunks;
+    std::vector<CountTask> tasks;
+    for (int chunk = 0; chunk < nchunks; ++chunk)
+        for (int k = 0; k < 3; ++k)
+            for (int64_t b = 0; b < blocks[k]; ++b) {
+                const int32_t first = (int32_t)(b * per_task[k]);
+                const int32_t count = (int32_t)std::min<int64_t>(per_task[k], c->n_items[k] - first);
+                if (k != ITEM_Y) tasks.push_back(CountTask{k, first, count, 0, chunk, nchunks});
+                tasks.push_back(CountTask{k, first, count, 1, chunk, nchunks});
+            }
+    if (tasks.size() > 0x7fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
     int r;
-    if ((r = dev_alloc(c, &c->d_PX, n + 1))) return r;
-    if ((r = dev_alloc(c, &c->d_PY, n + 1))) return r;
-    if ((r = dev_alloc(c, &c->d_CD, n + 1))) return r;
-    QS_CUDA(c, cudaMemcpy(c->d_PX, PX.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
-    QS_CUDA(c, cudaMemcpy(c->d_PY, PY.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
-    QS_CUDA(c, cudaMemcpy(c->d_CD, CD.data(), (n + 1) * 4, cudaMemcpyHostToDevice));
+    if ((r = dev_alloc(c, &c->d_tasks, tasks.size()))) return r;
+    if (!tasks.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks, tasks.data(), tasks.size() * sizeof(CountTask), cudaMemcpyHostToDevice));
+    c->n_tasks = (int)tasks.size();
+    c->tasks_for_m = c->m;
     return QS_OK;
 }
 
@@ -221,7 +255,7 @@ template <typename CINT>
 void launch_narrow(qs_ctx* c, uint64_t elems) {
     int blocks = (int)std::min<uint64_t>((elems + 255) / 256, (uint64_t)c->num_sms * 16);
     if (blocks < 1) blocks = 1;
-    qs_narrow_kernel<CINT><<<blocks, 256, 0, c->stream>>>(c->d_ws, (CINT*)c->d_table, elems);
+    qs_narrow_kernel<CINT><<<blocks, 256, 0, c->stream>>>(c->d_ws, (CINT*)c->d_table, elems, c->d_nA);
     c->launches++;
 }
 
@@ -238,11 +272,18 @@ int run_distances(qs_ctx* c) {
         if (r) { c->D_cap = 0; return r; }
         c->D_cap = need;
     }
+    if (c->m > c->class_cap) {
+        int r;
+        if ((r = dev_alloc(c, &c->d_class, (size_t)c->m))) { c->class_cap = 0; return r; }
+        if ((r = dev_alloc(c, &c->d_order, (size_t)c->m))) { c->class_cap = 0; return r; }
+        c->class_cap = c->m;
+    }
     QS_CUDA(c, cudaMemsetAsync(c->d_D, 0xFF, need * sizeof(__half), c->stream));   // 0xFFFF = NaN = "taxon missing"
     QS_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(int), c->stream));
     DistArgs da;
     da.node_off = c->d_off; da.parent = c->d_parent; da.leaf_id = c->d_leaf;
     da.m = (int)c->m; da.n = c->n; da.n_pad = c->n_pad; da.max_nodes = c->max_nodes; da.D = c->d_D; da.max_dist = c->d_flags;
+    da.tree_class = c->d_class;
     size_t smem = (size_t)8 * 4 * c->max_nodes + (size_t)((c->n + 31) / 32) * 4;
     if (smem > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "gene tree with %d nodes exceeds the distance kernel's shared-memory budget", c->max_nodes);
     QS_CUDA(c, cudaFuncSetAttribute(qs_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -251,54 +292,48 @@ int run_distances(qs_ctx* c) {
     qs_dist_kernel<<<grid, 256, smem, c->stream>>>(da);
     c->launches++;
     QS_CUDA(c, cudaGetLastError());
+    qs_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_class, (int)c->m, c->d_order, c->d_nA);
+    c->launches++;
+    QS_CUDA(c, cudaGetLastError());
     c->dist_valid = true;
     return QS_OK;
 }
 
-int run_count_small(qs_ctx* c) {
+int run_count_items(qs_ctx* c) {
     int r;
-    if (!c->d_PX && (r = build_small_tables(c))) return r;
+    if (!c->items_built && (r = build_items(c))) return r;
+    if (c->tasks_for_m != c->m && (r = build_tasks(c))) return r;
     const uint64_t nq = c->rank_end - c->rank_begin;
-    if (!c->d_ws && (r = dev_alloc(c, &c->d_ws, (size_t)nq * 3))) return r;
-    QS_CUDA(c, cudaMemsetAsync(c->d_ws, 0, (size_t)nq * 3 * sizeof(uint32_t), c->stream));
-    CountSmallArgs a;
-    a.D = c->d_D; a.ws = c->d_ws; a.PX = c->d_PX; a.PY = c->d_PY; a.CD = c->d_CD;
-    a.rank_base = c->rank_begin; a.n = c->n; a.n_pad = c->n_pad; a.m = (int)c->m;
-    a.d_begin = c->d_begin; a.d_end = c->d_end; a.NX = c->NX; a.NY = c->NY;
-    a.tree_bytes = (uint32_t)((size_t)c->n * c->n_pad * 2);
-    a.n_item_blocks = (std::max(c->NX, c->NY) + kSmallThreads - 1) / kSmallThreads;
-    if (a.n_item_blocks == 0) return QS_OK;
-    int tps = (int)(((size_t)c->smem_optin - 128) / (2 * (size_t)a.tree_bytes));
-    tps = std::max(1, std::min(tps, 8));
-    a.trees_per_stage = tps;
-    // tree chunks: <= 2048 trees each (fp16 counters), and enough tasks to fill whole waves of SMs
-    const int s_min = (int)((c->m + kMaxHalfExact - 1) / kMaxHalfExact);
-    int best_s = s_min; double best_eff = -1;
-    for (int s = s_min; s <= s_min + 12 && s <= std::max<int64_t>(1, c->m); ++s) {
-        int64_t tasks = (int64_t)a.n_item_blocks * s;
-        int64_t waves = (tasks + c->num_sms - 1) / c->num_sms;
-        double eff = (double)tasks / (double)(waves * c->num_sms);
-        if (eff > best_eff + 0.02) { best_eff = eff; best_s = s; }
+    if (!c->d_ws && (r = dev_alloc(c, &c->d_ws, (size_t)nq * QS_WS_SLOTS))) return r;
+    const uint32_t tree_bytes = (uint32_t)((size_t)c->n * c->n_pad * 2);
+    if (!c->d_nan_tree) {
+        if ((r = dev_alloc(c, &c->d_nan_tree, (size_t)tree_bytes / 2))) return r;
+        QS_CUDA(c, cudaMemsetAsync(c->d_nan_tree, 0xFF, tree_bytes, c->stream));
     }
-    int chunk = (int)((c->m + best_s - 1) / best_s);
-    chunk = std::min(kMaxHalfExact, ((chunk + tps - 1) / tps) * tps);
-    a.chunk_trees = chunk;
-    a.n_tree_chunks = (int)((c->m + chunk - 1) / chunk);
-    size_t smem = 128 + (size_t)CS_STAGES * tps * a.tree_bytes;
-    QS_CUDA(c, cudaFuncSetAttribute(qs_count_small_kernel<kSmallThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int grid = std::min(a.n_item_blocks * a.n_tree_chunks, c->num_sms);
+    QS_CUDA(c, cudaMemsetAsync(c->d_ws, 0, (size_t)nq * QS_WS_SLOTS * sizeof(uint32_t), c->stream));
+    QS_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
+    if (c->n_tasks == 0) return QS_OK;
+    CountItemsArgs a;
+    a.D = c->d_D; a.order = c->d_order; a.n_class_a = c->d_nA; a.nan_tree = c->d_nan_tree;
+    for (int k = 0; k < 3; ++k) a.items[k] = c->d_items[k];
+    a.tasks = c->d_tasks; a.n_tasks = c->n_tasks; a.task_counter = c->d_counter;
+    a.ws = c->d_ws; a.rank_base = c->rank_begin; a.n = c->n; a.n_pad = c->n_pad; a.m = (int)c->m;
+    a.d_begin = c->d_begin; a.d_end = c->d_end; a.tree_bytes = tree_bytes;
+    a.n_stages = (int)std::min<size_t>(CI_MAX_STAGES, ((size_t)c->smem_optin - 256) / (2 * (size_t)tree_bytes));
+    const size_t smem = 128 + (size_t)a.n_stages * 2 * tree_bytes;
+    QS_CUDA(c, cudaFuncSetAttribute(qs_count_items_kernel<kItemThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = std::min(c->n_tasks, c->num_sms);
     QS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));       // count_ms brackets the counting kernel alone
-    qs_count_small_kernel<kSmallThreads><<<grid, kSmallThreads, smem, c->stream>>>(a);
+    qs_count_items_kernel<kItemThreads><<<grid, kItemThreads, smem, c->stream>>>(a);
     QS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
     c->launches++;
     QS_CUDA(c, cudaGetLastError());
     // workspace -> CINT table
-    const uint64_t elems = nq * 3;
     switch (c->cint_bytes) {
-        case 1: launch_narrow<uint8_t>(c, elems); break;
-        case 2: launch_narrow<uint16_t>(c, elems); break;
-        case 4: launch_narrow<uint32_t>(c, elems); break;
-        default: launch_narrow<unsigned long long>(c, elems); break;
+        case 1: launch_narrow<uint8_t>(c, nq); break;
+        case 2: launch_narrow<uint16_t>(c, nq); break;
+        case 4: launch_narrow<uint32_t>(c, nq); break;
+        default: launch_narrow<unsigned long long>(c, nq); break;
     }
     QS_CUDA(c, cudaGetLastError());
     return QS_OK;
@@ -329,10 +364,9 @@ int make_dist_tensor_map(qs_ctx* c, CUtensorMap* tm, int box_rows, int box_cols)
 
 int build_tiles(qs_ctx* c) {
     std::vector<ushort4> tiles;
-    const int dlo = std::max(3, c->d_begin), dhi = c->d_end;       // d in [dlo, dhi)
-    for (int jd = dlo / 8; jd * 8 < dhi; ++jd) {
-        const int d_max = std::min(jd * 8 + 7, dhi - 1);
-        if (d_max < dlo) continue;
+    const int dlo = std::max(3, c->d_begin), dhi = c->d_end;       // d in [dlo, dhi); d-tiles are anchored at dlo
+    for (int jd = 0; dlo + jd * 8 < dhi; ++jd) {
+        const int d_max = std::min(dlo + jd * 8 + 7, dhi - 1);
         for (int ic = 0; ic * 16 <= d_max - 1; ++ic) {
             const int c_max = std::min(ic * 16 + 15, d_max - 1);
             if (c_max < 2) continue;
@@ -369,6 +403,8 @@ int run_count_tiled(qs_ctx* c) {
     CountTiledArgs a;
     memset(&a, 0, sizeof(a));
     a.tiles = c->d_tiles; a.n_tiles = c->n_tiles; a.n = c->n; a.m = (int)c->m; a.d_begin = c->d_begin; a.d_end = c->d_end;
+    a.order = c->d_order; a.n_class_a = c->d_nA; a.tile_counter = c->d_counter; a.d_tile_base = std::max(3, c->d_begin);
+    QS_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
     a.rank_base = c->rank_begin; a.scratch = c->d_scratch; a.cint_bytes = c->cint_bytes;
     a.table = (c->mode == QS_MODE_TABLE) ? c->d_table : nullptr;
     a.fused_score = (c->mode == QS_MODE_TABLE_FREE) ? 1 : 0;
@@ -383,7 +419,7 @@ int run_count_tiled(qs_ctx* c) {
         sa.pair_best = c->d_pair_best; sa.PB = nullptr; sa.n = c->n; sa.I = (int)I; sa.d_begin = c->d_begin; sa.d_end = c->d_end;
         sa.count_scale = c->fused_scale; sa.cint_mask = cint_mask(c->cint_bytes); sa.bifurcating = c->ref.bifurcating ? 1 : 0;
     }
-    const size_t smem = 128 + (size_t)CT_STAGES * CT_TPS * CT_TREE_BYTES;
+    const size_t smem = 128 + (size_t)CT_STAGES * CT_STAGE_BYTES;
     QS_CUDA(c, cudaFuncSetAttribute(qs_count_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     QS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
     qs_count_tiled_kernel<<<grid, CT_THREADS, smem, c->stream>>>(a, tm16x16, tm8x16, tm16x8);
@@ -634,6 +670,16 @@ int qs_create(qs_ctx** out, int n_taxa, int cint_bytes, int mode, int device, in
     if (cint_bytes != 1 && cint_bytes != 2 && cint_bytes != 4 && cint_bytes != 8) return QS_E_ARG;
     if (mode != QS_MODE_TABLE && mode != QS_MODE_TABLE_FREE) return QS_E_ARG;
     if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return QS_E_ARG;
+    if (device == QS_DEVICE_NONE) {
+        // host-only context: no CUDA call at all; only qs_set_reference / qs_score_finalize / qs_shard_range work on it
+        qs_ctx* c = new qs_ctx();
+        c->host_only = true; c->device = device; c->n = n_taxa; c->n_pad = (n_taxa + 7) / 8 * 8; c->cint_bytes = cint_bytes; c->mode = mode;
+        c->shard_index = shard_index; c->shard_count = shard_count;
+        shard_bounds(n_taxa, shard_index, shard_count, &c->d_begin, &c->d_end);
+        c->rank_begin = binom4((uint64_t)c->d_begin); c->rank_end = binom4((uint64_t)c->d_end);
+        *out = c;
+        return QS_OK;
+    }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { cudaGetLastError(); return QS_E_CUDA; }
     if (cudaSetDevice(device) != cudaSuccess) return QS_E_CUDA;
@@ -649,16 +695,19 @@ int qs_create(qs_ctx** out, int n_taxa, int cint_bytes, int mode, int device, in
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return QS_E_CUDA; }
     c->stream = c->own_stream;
     for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { free_all(c); delete c; return QS_E_CUDA; }
-    if (cudaMalloc((void**)&c->d_flags, 2 * sizeof(int)) != cudaSuccess) { free_all(c); delete c; return QS_E_CUDA; }
+    if (cudaMalloc((void**)&c->d_flags, 2 * sizeof(int)) != cudaSuccess || cudaMalloc((void**)&c->d_nA, sizeof(int32_t)) != cudaSuccess ||
+        cudaMalloc((void**)&c->d_counter, sizeof(int)) != cudaSuccess) { free_all(c); delete c; return QS_E_CUDA; }
     *out = c;
     return QS_OK;
 }
 
 int qs_destroy(qs_ctx* ctx) {
     if (!ctx) return QS_E_ARG;
-    cudaSetDevice(ctx->device);
-    cudaStreamSynchronize(ctx->stream);
-    free_all(ctx);
+    if (!ctx->host_only) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        free_all(ctx);
+    }
     delete ctx;
     return QS_OK;
 }
@@ -678,10 +727,11 @@ int qs_set_stream(qs_ctx* ctx, void* cuda_stream) {
 int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int32_t* parent_edge, const int32_t* leaf_lookup_id,
                      const int32_t* first_child, const int32_t* next_sibling) {
     if (!ctx || !parent || !parent_edge || !leaf_lookup_id || !first_child || !next_sibling) return QS_E_ARG;
-    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->host_only) QS_CUDA(ctx, cudaSetDevice(ctx->device));
     ctx->has_ref = false;
     int r = build_reference(ctx, n_nodes, parent, parent_edge, leaf_lookup_id, first_child, next_sibling);
     if (r) return r;
+    if (ctx->host_only) { ctx->has_ref = true; return QS_OK; }
     const size_t n = ctx->n;
     if ((r = dev_alloc(ctx, &ctx->d_lca, n * n))) return r;
     if ((r = dev_alloc(ctx, &ctx->d_idepth, (size_t)ctx->ref.n_inner))) return r;
@@ -710,6 +760,7 @@ int qs_num_trees(const qs_ctx* ctx, int64_t* n_trees) {
 
 int qs_add_trees(qs_ctx* ctx, int n_trees, const int64_t* node_offsets, const int32_t* parent, const int32_t* leaf_lookup_id) {
     if (!ctx || n_trees < 0 || !node_offsets || !parent || !leaf_lookup_id) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
     if (n_trees == 0) return QS_OK;
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (node_offsets[0] != 0) QS_FAIL(ctx, QS_E_TREE, "node_offsets[0] must be 0");
@@ -761,6 +812,7 @@ int qs_add_trees(qs_ctx* ctx, int n_trees, const int64_t* node_offsets, const in
 
 int qs_count(qs_ctx* ctx) {
     if (!ctx) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
     if (ctx->m == 0) QS_FAIL(ctx, QS_E_STATE, "no evaluation trees were added");
     if ((uint64_t)ctx->m > cint_mask(ctx->cint_bytes)) QS_FAIL(ctx, QS_E_ARG, "%lld trees do not fit a %d-byte counter", (long long)ctx->m, ctx->cint_bytes);
@@ -784,13 +836,16 @@ int qs_count(qs_ctx* ctx) {
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     if (nq) {
         const char* force = getenv("QS_FORCE_TILED");      // test hook: exercise the tiled kernel on small inputs
-        if (ctx->mode == QS_MODE_TABLE && small_path_ok(ctx) && !(force && force[0] == '1')) r = run_count_small(ctx);
+        if (ctx->mode == QS_MODE_TABLE && small_path_ok(ctx) && !(force && force[0] == '1')) r = run_count_items(ctx);
         else r = run_count_tiled(ctx);
         if (r) return r;
     }
     int flags[2] = {0, 0};
+    int32_t nA = 0;
     QS_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    QS_CUDA(ctx, cudaMemcpyAsync(&nA, ctx->d_nA, sizeof(nA), cudaMemcpyDeviceToHost, ctx->stream));
     QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_class_a = nA;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->dist_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->count_ms = ms;
@@ -808,6 +863,7 @@ int qs_score_num_pairs(const qs_ctx* ctx, int64_t* n_pairs) {
 
 int qs_score_partials(qs_ctx* ctx, int count_scale, double* lqic_partial, uint64_t* pair_sums) {
     if (!ctx || !lqic_partial || !pair_sums) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
     int r = run_score_scan(ctx, count_scale);
     if (r) return r;
@@ -828,11 +884,23 @@ int qs_score_finalize(qs_ctx* ctx, int exact_qp, const double* lqic_reduced, con
 
 int qs_score(qs_ctx* ctx, int count_scale, int exact_qp, double* lqic, double* qpic, double* eqpic) {
     if (!ctx || !lqic) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
     int r = run_score_scan(ctx, count_scale);
     if (r) return r;
     lqic_from_pairs(ctx, lqic);
     qp_from_pairs(ctx, (const uint64_t*)ctx->h_pair_sums.data(), exact_qp, qpic, eqpic);
+    return QS_OK;
+}
+
+int qs_shard_bounds(int n_taxa, int shard_index, int shard_count, int* s3_begin, int* s3_end, uint64_t* rank_begin, uint64_t* rank_end) {
+    if (n_taxa < 4 || shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return QS_E_ARG;
+    int b = 0, e = 0;
+    shard_bounds(n_taxa, shard_index, shard_count, &b, &e);
+    if (s3_begin) *s3_begin = b;
+    if (s3_end) *s3_end = e;
+    if (rank_begin) *rank_begin = binom4((uint64_t)b);
+    if (rank_end) *rank_end = binom4((uint64_t)e);
     return QS_OK;
 }
 
@@ -844,6 +912,7 @@ int qs_shard_range(const qs_ctx* ctx, uint64_t* rank_begin, uint64_t* rank_end) 
 
 int qs_get_counts(qs_ctx* ctx, uint64_t rank_begin, uint64_t rank_end, void* out) {
     if (!ctx || !out || rank_end < rank_begin) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
     if (ctx->mode != QS_MODE_TABLE) QS_FAIL(ctx, QS_E_STATE, "table-free context keeps no table");
     if (!ctx->counted) QS_FAIL(ctx, QS_E_STATE, "qs_count has not been called");
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -860,6 +929,7 @@ int qs_get_counts(qs_ctx* ctx, uint64_t rank_begin, uint64_t rank_end, void* out
 
 int qs_get_distances(qs_ctx* ctx, int64_t tree, uint16_t* out) {
     if (!ctx || !out) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
     if (!ctx->dist_valid) QS_FAIL(ctx, QS_E_STATE, "distance matrices are built by qs_count");
     if (tree < 0 || tree >= ctx->m) return QS_E_ARG;
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -877,6 +947,7 @@ int qs_get_distances(qs_ctx* ctx, int64_t tree, uint16_t* out) {
 
 int qs_write_raw_qic(qs_ctx* ctx, int count_scale, const char* const* taxon_names, const char* path) {
     if (!ctx || !taxon_names || !path) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
     if (ctx->mode != QS_MODE_TABLE || ctx->shard_count != 1) QS_FAIL(ctx, QS_E_STATE, "raw QIC needs a single-shard table context");
     if (!ctx->counted || !ctx->has_ref) QS_FAIL(ctx, QS_E_STATE, "needs qs_set_reference and qs_count");
     if (count_scale != 1 && count_scale != 2) return QS_E_ARG;
@@ -934,8 +1005,15 @@ int qs_launch_count(const qs_ctx* ctx, int64_t* n_launches) {
     return QS_OK;
 }
 
+int qs_tree_classes(const qs_ctx* ctx, int64_t* n_class_a, int64_t* n_class_b) {
+    if (!ctx || !n_class_a || !n_class_b) return QS_E_ARG;
+    *n_class_a = ctx->n_class_a; *n_class_b = ctx->m - ctx->n_class_a;
+    return QS_OK;
+}
+
 int qs_measure_alu_peak(qs_ctx* ctx, double* half2_pair_laneops_per_s, double* int32_laneops_per_s) {
     if (!ctx) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
     double h = 0, i = 0;
     cudaError_t e = ubench_alu_peak(ctx->num_sms, ctx->stream, &h, &i);

@@ -187,3 +187,84 @@ def test_table_free_mode_golden(name, golden, scale, suffix):
         want = g[key + suffix]
         fin = np.isfinite(want)
         assert np.array_equal(np.isinf(got), np.isinf(want)) and np.allclose(got[fin], want[fin], rtol=0, atol=1e-9)
+
+
+# ---- multi-GPU path: shards emulated sequentially on one GPU (integer sums and exact mins are
+# order-independent, so G shards must reproduce the 1-shard result bit for bit) ---------------------------
+
+def _run_shards(ref, flat, G, scale=1, mode=None):
+    from quartetscores_b200 import QS_MODE_TABLE
+    bits = cint_bits_for(flat.n_trees)
+    tables, lq_parts, sum_parts, ranges = [], [], [], []
+    fin = None
+    for g in range(G):
+        ctx = Context(ref.n_taxa, bits // 8, mode=QS_MODE_TABLE if mode is None else mode, shard_index=g, shard_count=G)
+        ctx.set_reference(ref)
+        if mode is not None:
+            ctx.set_count_scale(scale)
+        ctx.add_trees(flat)
+        ctx.count()
+        r0, r1 = ctx.shard_range()
+        ranges.append((r0, r1))
+        if mode is None:
+            tables.append(ctx.get_counts(r0, r1))
+        lq, sums = ctx.score_partials(scale)
+        lq_parts.append(lq)
+        sum_parts.append(sums)
+        if g == G - 1:
+            fin = ctx.score_finalize(np.minimum.reduce(lq_parts), np.add.reduce(sum_parts))
+        ctx.close()
+    return tables, ranges, fin
+
+
+@pytest.mark.parametrize("G", [2, 3, 8])
+@pytest.mark.parametrize("tiled", [False, True])
+def test_shards_reproduce_single_shard(G, tiled, monkeypatch):
+    if tiled:
+        monkeypatch.setenv("QS_FORCE_TILED", "1")
+    s = SyntheticInput(30, 300, 41, k_max=10, p_missing=0.05, p_contract=0.05, want_newick=False)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    with run_ctx(ref, s.flat) as ctx:
+        full = ctx.get_counts()
+        want = ctx.score(1)
+    tables, ranges, got = _run_shards(ref, s.flat, G)
+    assert ranges[0][0] == 0 and ranges[-1][1] == len(full) and all(ranges[i][1] == ranges[i + 1][0] for i in range(G - 1))
+    assert np.array_equal(np.concatenate(tables), full)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)                       # bit-identical, not just within tolerance
+
+
+@pytest.mark.parametrize("G", [2, 4])
+def test_table_free_shards_reproduce_single_shard(G):
+    from quartetscores_b200 import QS_MODE_TABLE_FREE
+    s = SyntheticInput(28, 200, 42, k_max=8, want_newick=False)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    with run_ctx(ref, s.flat) as ctx:
+        want = ctx.score(1)
+    _, _, got = _run_shards(ref, s.flat, G, mode=QS_MODE_TABLE_FREE)
+    for a, b in zip(got, want):
+        assert np.array_equal(a, b)
+
+
+def test_mixed_tree_classes_and_odd_counts():
+    """class A (complete, fully resolved) and class B trees interleaved, odd class sizes -> padded tree pairs."""
+    a = SyntheticInput(26, 151, 51, k_max=6, want_newick=False)                                   # all class A
+    b = SyntheticInput(26, 90, 51, k_max=6, p_missing=0.15, p_contract=0.1, want_newick=False)    # same reference, class B
+    assert a.ref_newick == b.ref_newick
+    ref = flatten_reference(parse_newick(a.ref_newick))
+    ctx = Context(ref.n_taxa, 1)
+    ctx.set_reference(ref)
+    # interleave: B-chunk, A, B-chunk
+    fb = b.flat
+    half = 45
+    ob = fb.node_offsets
+    ctx.add_trees_raw(ob[:half + 1], fb.parent[:ob[half]], fb.leaf_lookup_id[:ob[half]])
+    ctx.add_trees(a.flat)
+    ctx.add_trees_raw(ob[half:] - ob[half], fb.parent[ob[half]:], fb.leaf_lookup_id[ob[half]:])
+    ctx.count()
+    nA, nB = ctx.tree_classes()
+    assert nA >= 151 and nA + nB == 241 and nB > 0
+    got = ctx.get_counts().astype(np.uint32)
+    ctx.close()
+    want = (O.count_clades_compact(26, a.flat) + O.count_clades_compact(26, b.flat)) // 2
+    assert np.array_equal(got, want)
