@@ -284,7 +284,7 @@ def main():
     roofline = {
         "bound": "alu_issue", "achieved": achieved / 1e12, "peak": hset2_peak / 1e12, "unit": "Tlaneop/s", "frac": achieved / hset2_peak,
         "traffic": None,
-        "kernel": "qs_count_items_kernel" if n <= 165 else "qs_count_tiled_kernel", "kernel_ms": count_ms,
+        "kernel": "qs_count_rows_kernel", "kernel_ms": count_ms,
         "dist_kernel_ms": statistics.mean(t["dist_ms"] for t in kt), "score_kernel_ms": statistics.mean(t["score_ms"] for t in kt),
         "peak_source": "measured live on this GPU: HSET2 (fp16x2 compare -> mask) lane-op rate in the kernel's own 2xHSET2+IADD3 mix (qs_measure_alu_peak)",
         "algorithmic_laneops_per_eval": algo_laneops / my_evals,

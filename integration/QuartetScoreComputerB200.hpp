@@ -1,0 +1,213 @@
+// QuartetScoreComputerB200.hpp — drop-in replacement of the reference's QuartetScoreComputer<CINT>
+// (src/QuartetScoreComputer.hpp:43-51, :698-785) on top of libqscuda's C ABI (include/qscuda.h).
+//
+// Same template name, constructor arguments and methods as the reference class, so the reference's own
+// main (src/QuartetScores.cpp:114-147) compiles against it unchanged — see integration/main_b200.cpp and
+// INTEGRATION.md.  Host side only: genesis still parses the Newick files and numbers nodes/edges, this class
+// flattens the trees and hands them to the GPU library.  All counting and scoring happens
+// in libqscuda.so; there is no CPU fallback (a missing GPU is a std::runtime_error).
+//
+// Multi-GPU: one process, one context per visible device (or $QS_NUM_GPUS), each owning a shard of the quartet
+// rank space and driven by its own host thread; the per-shard partials are reduced on the host (min for
+// LQ-IC, sum for the pair sums) — no collective is needed inside a single process.
+#pragma once
+
+#include "genesis/genesis.hpp"
+#include "qscuda.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstdlib>
+#include <iostream>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+namespace qsb200 {
+
+using namespace genesis;
+using namespace genesis::tree;
+
+struct FlatTree {
+    std::vector<int32_t> parent, parent_edge, leaf_id, first_child, next_sibling;
+};
+
+// genesis numbers nodes parent-first (root = 0), so parent[i] < i holds
+inline void flatten_tree(Tree const& tree, FlatTree& f, bool want_children,
+                         std::unordered_map<std::string, int32_t> const* name_to_id, std::vector<int32_t> const* node_to_id) {
+    const size_t N = tree.node_count();
+    f.parent.assign(N, -1); f.parent_edge.assign(N, -1); f.leaf_id.assign(N, -1);
+    if (want_children) { f.first_child.assign(N, -1); f.next_sibling.assign(N, -1); }
+    if (tree.root_node().index() != 0) throw std::runtime_error("flatten_tree: root node index is not 0");
+    for (size_t i = 0; i < N; ++i) {
+        TreeNode const& node = tree.node_at(i);
+        const bool is_root = (i == 0);
+        if (!is_root) {
+            f.parent[i] = (int32_t)node.primary_link().outer().node().index();
+            f.parent_edge[i] = (int32_t)node.primary_link().edge().index();
+            if (f.parent[i] >= (int32_t)i) throw std::runtime_error("flatten_tree: node numbering is not parent-first");
+        }
+        if (node.is_leaf()) {
+            if (node_to_id) f.leaf_id[i] = (*node_to_id)[i];
+            else f.leaf_id[i] = name_to_id->at(node.data<DefaultNodeData>().name);   // std::out_of_range on an unknown taxon, as QuartetCounterLookup.hpp:218
+        }
+        if (want_children && !node.is_leaf()) {
+            // children in Newick order: the links after the primary link; the root's primary link is its first child
+            TreeLink const* first = is_root ? &tree.root_link() : &node.primary_link().next();
+            TreeLink const* stop = is_root ? &tree.root_link() : &node.primary_link();
+            int32_t prev = -1;
+            TreeLink const* l = first;
+            do {
+                const int32_t ch = (int32_t)l->outer().node().index();
+                if (prev < 0) f.first_child[i] = ch; else f.next_sibling[prev] = ch;
+                prev = ch;
+                l = &l->next();
+            } while (l != stop);
+        }
+    }
+}
+
+inline void qs_check(qs_ctx* ctx, int rc, const char* what) {
+    if (rc == QS_OK) return;
+    std::string msg = std::string(what) + ": " + (ctx ? qs_last_error(ctx) : qs_strerror(rc));
+    if (rc == QS_E_MEMORY) throw std::runtime_error("Insufficient memory! " + msg);      // wording of QuartetScoreComputer.hpp:735-737
+    throw std::runtime_error(msg);
+}
+
+template<typename CINT>
+class QuartetScoreComputer {
+public:
+    QuartetScoreComputer(Tree const& refTree, const std::string& evalTreesPath, size_t m, bool verboseOutput, bool savemem);
+    ~QuartetScoreComputer() { for (auto c : ctxs) if (c) qs_destroy(c); }
+    QuartetScoreComputer(QuartetScoreComputer const&) = delete;
+    QuartetScoreComputer& operator=(QuartetScoreComputer const&) = delete;
+
+    std::vector<double> getLQICScores() { return LQICScores; }
+    std::vector<double> getQPICScores() { return QPICScores; }
+    std::vector<double> getEQPICScores() { return EQPICScores; }
+    void printRawQICScores(Tree const& refTree, const std::string& rawFilePath);
+
+private:
+    std::vector<qs_ctx*> ctxs;
+    std::vector<std::string> taxa;     // label of every lookup id
+    std::vector<double> LQICScores, QPICScores, EQPICScores;
+    int count_scale = 1;
+    bool verbose = false;
+};
+
+template<typename CINT>
+QuartetScoreComputer<CINT>::QuartetScoreComputer(Tree const& refTree, const std::string& evalTreesPath, size_t m, bool verboseOutput, bool savemem)
+    : verbose(verboseOutput) {
+    (void)m;
+    std::cout << "There are " << m << " evaluation trees.\n";
+    // taxon (lookup) ids: position in the reference tree's Euler-tour leaf order (QuartetCounterLookup.hpp:249-258)
+    std::vector<int32_t> refNodeToId(refTree.node_count(), -1);
+    std::unordered_map<std::string, int32_t> nameToId;
+    for (auto it : eulertour(refTree)) {
+        if (it.node().is_leaf() && refNodeToId[it.node().index()] < 0) {
+            const int32_t id = (int32_t)taxa.size();
+            refNodeToId[it.node().index()] = id;
+            nameToId[it.node().template data<DefaultNodeData>().name] = id;
+            taxa.push_back(it.node().template data<DefaultNodeData>().name);
+        }
+    }
+    const int n = (int)taxa.size();
+    std::cout << "The reference tree has " << n << " taxa.\n";
+    FlatTree ref;
+    flatten_tree(refTree, ref, true, nullptr, &refNodeToId);
+
+    // the -s table of the reference stores doubled, CINT-wrapped counts; same scores otherwise
+    count_scale = savemem ? 2 : 1;
+
+    // one context per GPU
+    int n_gpus = 1;
+    if (const char* env = std::getenv("QS_NUM_GPUS")) n_gpus = std::max(1, std::atoi(env));
+    const int mode = savemem ? QS_MODE_TABLE_FREE : QS_MODE_TABLE;
+    ctxs.assign(n_gpus, nullptr);
+    for (int g = 0; g < n_gpus; ++g) {
+        qs_check(nullptr, qs_create(&ctxs[g], n, (int)sizeof(CINT), mode, g, g, n_gpus), "qs_create");
+        qs_check(ctxs[g], qs_set_count_scale(ctxs[g], count_scale), "qs_set_count_scale");
+        qs_check(ctxs[g], qs_set_reference(ctxs[g], (int)refTree.node_count(), ref.parent.data(), ref.parent_edge.data(), ref.leaf_id.data(),
+                                           ref.first_child.data(), ref.next_sibling.data()), "qs_set_reference");
+    }
+
+    // stream the evaluation trees: parse (genesis), flatten, hand over in batches
+    std::chrono::steady_clock::time_point begin = std::chrono::steady_clock::now();
+    {
+        utils::InputStream instream(utils::make_unique<utils::FileInputSource>(evalTreesPath));
+        DefaultTreeNewickReader reader;                        // kept alive: the iterator's reader copy refers to its plugin
+        auto itTree = NewickInputIterator(instream, reader);
+        std::vector<int64_t> off{0};
+        std::vector<int32_t> par, leaf;
+        FlatTree ft;
+        auto flush = [&]() {
+            if (off.size() <= 1) return;
+            for (auto c : ctxs) qs_check(c, qs_add_trees(c, (int)off.size() - 1, off.data(), par.data(), leaf.data()), "qs_add_trees");
+            off.assign(1, 0); par.clear(); leaf.clear();
+        };
+        while (itTree) {
+            flatten_tree(*itTree, ft, false, &nameToId, nullptr);
+            par.insert(par.end(), ft.parent.begin(), ft.parent.end());
+            leaf.insert(leaf.end(), ft.leaf_id.begin(), ft.leaf_id.end());
+            off.push_back((int64_t)par.size());
+            if (par.size() > (size_t(1) << 22)) flush();
+            ++itTree;
+        }
+        flush();
+    }
+    std::cout << "Finished parsing evaluation trees.\n";
+
+    // count + partial scores per shard (one host thread per GPU), reduce on the host
+    int64_t n_pairs = 0;
+    qs_check(ctxs[0], qs_score_num_pairs(ctxs[0], &n_pairs), "qs_score_num_pairs");
+    const size_t E = refTree.edge_count();
+    std::vector<std::vector<double>> lq(n_gpus, std::vector<double>(E));
+    std::vector<std::vector<uint64_t>> sums(n_gpus, std::vector<uint64_t>((size_t)n_pairs * 3));
+    std::vector<std::string> errors(n_gpus);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < n_gpus; ++g)
+        workers.emplace_back([&, g]() {
+            try {
+                qs_check(ctxs[g], qs_count(ctxs[g]), "qs_count");
+                qs_check(ctxs[g], qs_score_partials(ctxs[g], count_scale, lq[g].data(), sums[g].data()), "qs_score_partials");
+            } catch (std::exception const& e) { errors[g] = e.what(); }
+        });
+    for (auto& w : workers) w.join();
+    for (auto& e : errors) if (!e.empty()) throw std::runtime_error(e);
+    std::chrono::steady_clock::time_point end = std::chrono::steady_clock::now();
+    std::cout << "Finished counting quartets.\nIt took: " << std::chrono::duration_cast<std::chrono::microseconds>(end - begin).count()
+              << " microseconds.\n";
+    begin = std::chrono::steady_clock::now();
+    for (int g = 1; g < n_gpus; ++g) {
+        for (size_t e = 0; e < E; ++e) lq[0][e] = std::min(lq[0][e], lq[g][e]);
+        for (size_t k = 0; k < sums[0].size(); ++k) sums[0][k] += sums[g][k];
+    }
+    LQICScores.assign(E, std::numeric_limits<double>::infinity());
+    QPICScores.assign(E, std::numeric_limits<double>::infinity());
+    EQPICScores.assign(E, std::numeric_limits<double>::infinity());
+    qs_check(ctxs[0], qs_score_finalize(ctxs[0], 0, lq[0].data(), sums[0].data(), LQICScores.data(), QPICScores.data(), EQPICScores.data()), "qs_score_finalize");
+    if (!is_bifurcating(refTree)) {       // QuartetScoreComputer.hpp:760-765: only LQ-IC for a multifurcating reference
+        std::cout << "The reference tree is multifurcating.\n";
+        QPICScores.clear();
+        EQPICScores.clear();
+    } else {
+        std::cout << "The reference tree is bifurcating.\n";
+    }
+    end = std::chrono::steady_clock::now();
+    std::cout << "Finished computing scores.\nIt took: " << std::chrono::duration_cast<std::chrono::microseconds>(end - begin).count()
+              << " microseconds.\n";
+}
+
+template<typename CINT>
+void QuartetScoreComputer<CINT>::printRawQICScores(Tree const& refTree, const std::string& rawFilePath) {
+    (void)refTree;
+    if (ctxs.size() != 1) throw std::runtime_error("printRawQICScores needs the whole table on one GPU: run with QS_NUM_GPUS=1 and without -s");
+    std::vector<const char*> names;
+    for (auto const& t : taxa) names.push_back(t.c_str());
+    qs_check(ctxs[0], qs_write_raw_qic(ctxs[0], count_scale, names.data(), rawFilePath.c_str()), "qs_write_raw_qic");
+}
+
+}  // namespace qsb200

@@ -1,47 +1,50 @@
-// count_roles.cuh — the per-(thread, tree pair) inner steps shared by both counting kernels.
+// count_roles.cuh — the per-(thread, tree) inner steps of the counting kernels.
 //
-// Four-point test in "fixed pair" form (derivation in count_items.cuh).  For a fixed taxon pair (p,q)
-// and G_pq(t) = D[q][t] - D[p][t]:   G(u) > G(v)  <=>  the tree displays up|vq.
+// Four-point test in "fixed pair" form (derivation in count_rows.cuh).  For a fixed taxon pair (p,q) and
+// G_pq(t) = D[q][t] - D[p][t]:   G(u) > G(v)  <=>  the tree displays up|vq.
 //
-// Instruction mix (measured on B200, profiles/r01_b_ubench_pipes.txt):
-//   * compare: HSET2.GT / HSET2.LT on packed fp16x2 (distances are small integers, exact in fp16) with
-//     an INTEGER MASK result (0xFFFF per true half).  A missing taxon is NaN -> ordered compare false.
-//     HSET2 issues at 2.0 warp-instr/clk/SM; it is the pipe this kernel is bound by.
-//   * accumulate: ONE three-input integer add per TWO masks (acc = acc - m0 - m1, SASS IADD3 with both
-//     operands negated).  Subtracting 0xFFFF from a 16-bit half adds 1 to it and borrows from the
-//     upper half, so after L low-half hits and H high-half hits   acc = L + 65536*(H - L)  (mod 2^32),
-//     which decode() inverts exactly while L,H <= 65535.  The two masks of one add belong to the same
-//     counter and two different gene trees, so trees are processed in pairs.
-//     HSET2 x2 + IADD3 sustains 2.96 warp-instr/clk/SM = 1.97 compares/clk/SM, against 1.6 for the
-//     fp16 HSET2.BF + HADD2 pair used before (issue-limited at 3.2) — and the counters now hold 65535
-//     trees instead of 2048.
+// Instruction mix, chosen from measurements on B200 (profiles/r01_b_ubench_pipes.txt,
+// profiles/r01_c_ubench_loop.txt and the ncu captures next to them):
+//   * compare: HSET2.BF.GT / .LT on packed fp16x2 (distances are small integers, exact in fp16): two
+//     quartets per lane, result 1.0 / 0.0 per half.  A missing taxon is NaN -> ordered compare false.
+//     HSET2 runs on the ALU pipe (0.5 warp-instr/clk/SMSP).
+//   * accumulate: HADD2 on the fp16 pipe (0.5 warp-instr/clk/SMSP).  Counters start at -2048 so that a
+//     chunk may hold 4096 trees (fp16 represents every integer in [-2048, 2048] exactly).
+//   The alternative "integer mask + one three-input IADD3 per two masks" needs fewer instructions and looked
+//   better in an isolated microbenchmark, but IADD3 shares the ALU pipe with HSET2: in the real loop ncu
+//   shows pipe_alu at 97 % and 1.22 compares/clk/SM, against 1.46 for HSET2.BF + HADD2 (ALU 79 %,
+//   fp16 83 %, issue 84 %) — so the two half-rate pipes are loaded evenly on purpose.
 #pragma once
 #include "common.cuh"
 
 namespace qs {
 
-constexpr int QS_MAX_CHUNK_TREES = 65534;   // even, <= 65535: capacity of one 16-bit counter half
+constexpr int QS_MAX_CHUNK_TREES = 4096;
+constexpr float QS_COUNTER_BIAS = 2048.f;
 
-struct XCounters { uint32_t gt[8][4], lt[8][4]; };   // 8 (b) x 8 (a, packed in pairs): G(a)>G(b), G(a)<G(b)
-struct GCounters { uint32_t gt[8][4]; };             // 8 x 8, G(u)>G(v) only
+struct XCounters { __half2 gt[8][4], lt[8][4]; };   // 8 (v) x 8 (u, packed in pairs): G(u)>G(v), G(u)<G(v)
+struct GCounters { __half2 gt[8][4]; };             // 8 x 8, G(u)>G(v) only
 
 __device__ __forceinline__ void zero(XCounters& x) {
+    const __half2 z = __float2half2_rn(-QS_COUNTER_BIAS);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int p = 0; p < 4; ++p) { x.gt[j][p] = 0u; x.lt[j][p] = 0u; }
+        for (int p = 0; p < 4; ++p) { x.gt[j][p] = z; x.lt[j][p] = z; }
 }
 __device__ __forceinline__ void zero(GCounters& y) {
+    const __half2 z = __float2half2_rn(-QS_COUNTER_BIAS);
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
-        for (int p = 0; p < 4; ++p) y.gt[j][p] = 0u;
+        for (int p = 0; p < 4; ++p) y.gt[j][p] = z;
 }
 
-// packed counter -> (hits in the low half, hits in the high half)
-__device__ __forceinline__ void decode(uint32_t acc, uint32_t& lo, uint32_t& hi) {
-    lo = acc & 0xFFFFu;
-    hi = ((acc >> 16) + lo) & 0xFFFFu;
+// packed counter -> (hits of the low half, hits of the high half)
+__device__ __forceinline__ void decode(__half2 acc, uint32_t& lo, uint32_t& hi) {
+    const float2 f = __half22float2(acc);
+    lo = (uint32_t)(f.x + QS_COUNTER_BIAS);
+    hi = (uint32_t)(f.y + QS_COUNTER_BIAS);
 }
 
 __device__ __forceinline__ void sub4(__half2 (&g)[4], const uint4& hi, const uint4& lo) {
@@ -53,47 +56,43 @@ __device__ __forceinline__ void sub4(__half2 (&g)[4], const uint4& hi, const uin
 struct BlockRows { uint4 pu, qu, pv, qv; };
 
 // role X (pair (c,d) fixed, u = a, v = b): G(a) > G(b) -> ac|bd (slot 1),  G(a) < G(b) -> ad|bc (slot 2)
-__device__ __forceinline__ void step_gt_lt(XCounters& x, const BlockRows& r0, const BlockRows& r1) {
-    __half2 u0[4], v0[4], u1[4], v1[4];
-    sub4(u0, r0.qu, r0.pu); sub4(v0, r0.qv, r0.pv);
-    sub4(u1, r1.qu, r1.pu); sub4(v1, r1.qv, r1.pv);
+__device__ __forceinline__ void step_gt_lt(XCounters& x, const BlockRows& r) {
+    __half2 u[4], v[4];
+    sub4(u, r.qu, r.pu);
+    sub4(v, r.qv, r.pv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const __half2 b0 = (j & 1) ? __high2half2(v0[j >> 1]) : __low2half2(v0[j >> 1]);
-        const __half2 b1 = (j & 1) ? __high2half2(v1[j >> 1]) : __low2half2(v1[j >> 1]);
+        const __half2 b = (j & 1) ? __high2half2(v[j >> 1]) : __low2half2(v[j >> 1]);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            x.gt[j][p] = x.gt[j][p] - __hgt2_mask(u0[p], b0) - __hgt2_mask(u1[p], b1);
-            x.lt[j][p] = x.lt[j][p] - __hlt2_mask(u0[p], b0) - __hlt2_mask(u1[p], b1);
+            x.gt[j][p] = __hadd2(x.gt[j][p], __hgt2(u[p], b));
+            x.lt[j][p] = __hadd2(x.lt[j][p], __hlt2(u[p], b));
         }
     }
 }
 
-// G(u) > G(v) only: role Y (pair (b,c) fixed, u = a, v = d: ab|cd, slot 0) and the diagonal blocks of role X
-__device__ __forceinline__ void step_gt(GCounters& y, const BlockRows& r0, const BlockRows& r1) {
-    __half2 u0[4], v0[4], u1[4], v1[4];
-    sub4(u0, r0.qu, r0.pu); sub4(v0, r0.qv, r0.pv);
-    sub4(u1, r1.qu, r1.pu); sub4(v1, r1.qv, r1.pv);
+// G(u) > G(v) only: role Y (pair (b,c) fixed, u = a, v = d: ab|cd, slot 0)
+__device__ __forceinline__ void step_gt(GCounters& y, const BlockRows& r) {
+    __half2 u[4], v[4];
+    sub4(u, r.qu, r.pu);
+    sub4(v, r.qv, r.pv);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const __half2 b0 = (j & 1) ? __high2half2(v0[j >> 1]) : __low2half2(v0[j >> 1]);
-        const __half2 b1 = (j & 1) ? __high2half2(v1[j >> 1]) : __low2half2(v1[j >> 1]);
+        const __half2 b = (j & 1) ? __high2half2(v[j >> 1]) : __low2half2(v[j >> 1]);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) y.gt[j][p] = y.gt[j][p] - __hgt2_mask(u0[p], b0) - __hgt2_mask(u1[p], b1);
+        for (int p = 0; p < 4; ++p) y.gt[j][p] = __hadd2(y.gt[j][p], __hgt2(u[p], b));
     }
 }
 
 // diagonal block of role X (u and v are the same 8 taxa): G(x) > G(y) for all ordered pairs; one load per row
-__device__ __forceinline__ void step_gt_diag(GCounters& y, const uint4& p0, const uint4& q0, const uint4& p1, const uint4& q1) {
-    __half2 u0[4], u1[4];
-    sub4(u0, q0, p0);
-    sub4(u1, q1, p1);
+__device__ __forceinline__ void step_gt_diag(GCounters& y, const uint4& p, const uint4& q) {
+    __half2 u[4];
+    sub4(u, q, p);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        const __half2 b0 = (j & 1) ? __high2half2(u0[j >> 1]) : __low2half2(u0[j >> 1]);
-        const __half2 b1 = (j & 1) ? __high2half2(u1[j >> 1]) : __low2half2(u1[j >> 1]);
+        const __half2 b = (j & 1) ? __high2half2(u[j >> 1]) : __low2half2(u[j >> 1]);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) y.gt[j][p] = y.gt[j][p] - __hgt2_mask(u0[p], b0) - __hgt2_mask(u1[p], b1);
+        for (int pp = 0; pp < 4; ++pp) y.gt[j][pp] = __hadd2(y.gt[j][pp], __hgt2(u[pp], b));
     }
 }
 

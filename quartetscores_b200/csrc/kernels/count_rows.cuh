@@ -1,0 +1,388 @@
+// count_rows.cuh — the quartet counting kernel (any n).
+//
+// Replaces the reference hot loop QuartetCounterLookup::updateQuartetsThreeClades
+// (src/QuartetCounterLookup.hpp:66-106) + countQuartets (:197-238).  Instead of enumerating clades per
+// tree and scattering increments into an n^4 table, every thread OWNS a fixed 8 x 8 block of quartets,
+// keeps their topology counters in registers across all gene trees of its chunk, and decides each
+// (quartet, tree) with the four-point condition on the tree's distance matrix D.  Only the matrix ROWS a
+// task needs are staged in shared memory, by TMA bulk copies (cp.async.bulk, SASS UBLKCP) through an
+// mbarrier pipeline.
+//
+// Four-point test in "fixed pair" form.  For taxa p,q define G_pq(t) = D[q][t] - D[p][t].  For a tree
+// metric, G_pq(u) > G_pq(v)  <=>  D_up + D_vq < D_uq + D_vp  <=>  the tree displays up|vq (the two
+// larger pair sums of a tree metric are equal, so one strict inequality decides the topology;
+// ties = unresolved or the third topology).  With sorted ids a<b<c<d and the table slots
+// 0 = ab|cd, 1 = ac|bd, 2 = ad|bc (src/quartet_lookup_table.hpp:87-111):
+//   role X, pair (c,d) fixed:  G_cd(a) > G_cd(b) -> slot 1,   G_cd(a) < G_cd(b) -> slot 2
+//   role Y, pair (b,c) fixed:  G_bc(a) > G_bc(d) -> slot 0
+// A missing taxon makes D = NaN in its row/column, G = NaN, and every ordered compare false, so such
+// (quartet, tree) pairs count nothing — exactly the reference, where absent taxa are never enumerated.
+//
+// Fully resolved trees need no role Y.  The distance kernel classifies every gene tree: class A = all n
+// taxa present and no node of degree > 3, i.e. every quartet is resolved in it, so
+// slot0 + slot1 + slot2 = 1 per tree and slot 0 = |A| - slot1_A - slot2_A.  Class-A trees (first in the
+// class-sorted order[]) only run role X: 2 compares per quartet x tree instead of 3.
+//
+// Work items (8 x 8 register blocks = 64 quartets), each kind enumerated in one global order:
+//   XO  (c; d; a-block ia < b-block ib): G(a)>G(b) and G(a)<G(b)                               1 item / thread
+//   XD  (c; d; diagonal block i, a and b in the same block): all ordered pairs, G(x)>G(y) only;
+//       x<y gives slot 1 of (x,y), x>y gives slot 2 of (y,x) — half the cost of a full block   2 items / thread
+//   Y   (b; c; d-block; a-block): G(a)>G(d)                                                    2 items / thread
+// so a thread always carries 64 packed counter registers and issues 64 HSET2 + 64 HADD2 per tree.  A task
+// is a run of up to 512 thread-items of one kind; consecutive items share matrix rows, and the host records
+// the rows a task touches as at most three contiguous row ranges.  Only those rows are staged per tree
+// (n = 100: ~3 KB instead of the 21 KB matrix; n = 1000: 4 KB for 32,768 quartets = 0.12 B per evaluation).
+// Tasks x tree classes x tree chunks are handed to persistent CTAs through an atomic counter.  Counters are
+// flushed once per task straight into the CINT table with red.global.add on 32-bit words (two uint16 / four
+// uint8 fields per word; all arithmetic is mod 2^32 and every field ends non-negative and in range, so
+// transient carries between fields cancel).
+#pragma once
+#include "common.cuh"
+#include "count_roles.cuh"
+
+namespace qs {
+
+enum { ITEM_XO = 0, ITEM_XD = 1, ITEM_Y = 2 };
+
+struct RowTask {
+    int32_t kind;           // ITEM_*
+    int32_t ne;             // number of items (<= threads * items-per-thread)
+    int64_t e0;             // first item in the kind's global enumeration
+    int32_t rstart[3];      // up to three contiguous ranges of matrix rows the items touch ...
+    int32_t rcount[3];      // ... staged back to back in shared memory
+};
+
+// prefix tables of the three enumerations (device pointers in the kernel arguments, host vectors in qscuda.cu)
+struct EnumTables {
+    const int64_t* PXO;     // [n+1] XO items with c' < c
+    const int64_t* PXD;     // [n+1] XD items with c' < c
+    const int64_t* PY;      // [n+1] Y items with b' < b
+    const int64_t* CD;      // [n+1] d-blocks of role Y over c' < c
+    int xo_diag;            // 1: diagonal blocks are ordinary XO items (ia <= ib) and there are no XD items (large n, where
+                            //    XD tasks would be starved of items by the row budget and diagonal blocks are a few % of the work)
+};
+
+struct CountRowsArgs {
+    const __half* D;            // [m][n][n_pad] fp16, NaN = missing, indexed by ORIGINAL tree index
+    const int32_t* order;       // [m] class-sorted tree order: class A first
+    const int32_t* n_class_a;   // device scalar |A|
+    const RowTask* tasks;       // X tasks [0, n_x), then Y tasks [n_x, n_x + n_y)
+    EnumTables E;
+    int n_x, n_y;
+    int chunk_trees;            // target trees per chunk (<= QS_MAX_CHUNK_TREES)
+    int* task_counter;          // zeroed by the caller
+    void* table;                // CINT [(rank - rank_base)][3], initialised by qs_table_init_kernel
+    int cint_bytes;
+    uint64_t rank_base;
+    int n, n_pad, m;
+    int d_begin, d_end;         // shard: quartets with d in [d_begin, d_end)
+    int n_stages, trees_per_stage;
+    uint32_t row_bytes;         // n_pad * 2
+    uint32_t slot_bytes;        // shared-memory bytes reserved per tree = (max rows of a task) * row_bytes
+};
+
+constexpr int CR_THREADS = 512;
+constexpr int CR_MAX_STAGES = 8;
+constexpr int CR_MAX_TPS = 4;
+
+// ---- the enumerations (shared by the host task builder and the kernel) ---------------------------------------
+__host__ __device__ __forceinline__ int cr_nxd(int c, int xo_diag) { return (!xo_diag && c >= 2) ? ((c - 2) >> 3) + 1 : 0; }   // blocks with two taxa below c
+__host__ __device__ __forceinline__ int cr_nxo(int c, int xo_diag) {                                                          // b-blocks below c, ia < ib
+    const int nb = (c + 7) >> 3;
+    return nb * (nb - 1) / 2 + (xo_diag ? cr_nxd(c, 0) : 0);                                                                   // (+ the diagonal blocks)
+}
+__host__ __device__ __forceinline__ int cr_dlo(int c, int d_begin) { return c + 1 > d_begin ? c + 1 : d_begin; }
+__host__ __device__ __forceinline__ int cr_ndb(int c, int d_begin, int d_end) {                                    // d-blocks (of 8) above c
+    const int dlo = cr_dlo(c, d_begin);
+    return dlo < d_end ? ((d_end - 1) >> 3) - (dlo >> 3) + 1 : 0;
+}
+// largest x in [lo,hi) with P[x] <= key  (P non-decreasing, P[lo] <= key)
+__host__ __device__ __forceinline__ int cr_ub(const int64_t* P, int lo, int hi, int64_t key) {
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (P[mid] <= key) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+// item e of kind XO / XD -> (c, d, block index j inside the (c,d) pair)
+__host__ __device__ __forceinline__ void cr_decode_x(const int64_t* P, int kind, int xo_diag, int64_t e, int n, int d_begin, int& c, int& d, int& j) {
+    c = cr_ub(P, 0, n, e);
+    const int64_t r = e - P[c];
+    const int cnt = kind == ITEM_XO ? cr_nxo(c, xo_diag) : cr_nxd(c, xo_diag);
+    d = cr_dlo(c, d_begin) + (int)(r / cnt);
+    j = (int)(r % cnt);
+}
+// item e of kind Y -> (b, c, a-block ia, d-block id)
+__host__ __device__ __forceinline__ void cr_decode_y(const EnumTables& E, int64_t e, int n, int d_begin, int& b, int& c, int& ia, int& id) {
+    b = cr_ub(E.PY, 0, n, e);
+    const int64_t r = e - E.PY[b];
+    const int na = (b + 7) >> 3;
+    ia = (int)(r % na);
+    const int64_t target = E.CD[b + 1] + r / na;
+    c = cr_ub(E.CD, b + 1, n, target);
+    id = (cr_dlo(c, d_begin) >> 3) + (int)(target - E.CD[c]);
+}
+
+// add v (mod 2^32, may stand for a negative number) to element `elem` of the CINT table
+__device__ __forceinline__ void table_red(void* table, int cint_bytes, uint64_t elem, uint32_t v) {
+    if (v == 0u) return;
+    switch (cint_bytes) {
+        case 1: atomicAdd(reinterpret_cast<uint32_t*>(table) + (elem >> 2), v << (8u * (uint32_t)(elem & 3))); break;
+        case 2: atomicAdd(reinterpret_cast<uint32_t*>(table) + (elem >> 1), v << (16u * (uint32_t)(elem & 1))); break;
+        case 4: atomicAdd(reinterpret_cast<uint32_t*>(table) + elem, v); break;
+        default: atomicAdd(reinterpret_cast<unsigned long long*>(table) + elem, (unsigned long long)(long long)(int32_t)v); break;
+    }
+}
+
+struct RowPipe {
+    uint64_t* full;             // [CR_MAX_STAGES] tx barriers
+    int* done;                  // [CR_MAX_STAGES] warps finished with the stage
+    unsigned char* bufs;
+    uint32_t stage_bytes;
+    uint32_t phase;             // bit s = parity to wait for on full[s]
+};
+
+// Stream the trees [t0,t1) of the class-sorted order through the pipeline, trees_per_stage at a time; f(base)
+// is called once per tree with the shared-memory address of its staged rows.  Warps run independently: the
+// last warp to finish a stage refills it (no CTA-wide barrier inside the loop).
+template <class F>
+__device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, const RowTask& T, int t0, int t1, F&& f) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tps = a.trees_per_stage;
+    const int nst = (t1 - t0 + tps - 1) / tps;
+    const size_t tree_elems = (size_t)a.n * a.n_pad;
+    const uint32_t task_slot = (uint32_t)(T.rcount[0] + T.rcount[1] + T.rcount[2]) * a.row_bytes;       // bytes actually staged per tree
+    // lanes 0..tps-1 of the calling warp copy the rows of the trees of stage st (ids in `tree`, -1 = none)
+    auto issue = [&](int st, int buf, int tree) {
+        const int nt = min(tps, (t1 - t0) - st * tps);
+        if (lane == 0) mbar_expect_tx(&P.full[buf], (uint32_t)nt * task_slot);
+        __syncwarp();
+        if (lane < nt) {
+            unsigned char* dst = P.bufs + (size_t)buf * P.stage_bytes + (size_t)lane * a.slot_bytes;
+            const __half* src = a.D + (size_t)tree * tree_elems;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (T.rcount[k] > 0) bulk_g2s(dst, src + (size_t)T.rstart[k] * a.n_pad, (uint32_t)T.rcount[k] * a.row_bytes, &P.full[buf]);
+                dst += (size_t)T.rcount[k] * a.row_bytes;
+            }
+        }
+    };
+    auto tree_of = [&](int st) -> int {      // tree id this lane would copy for stage st
+        const int t = t0 + st * tps + lane;
+        return (lane < tps && st < nst && t < t1) ? a.order[t] : -1;
+    };
+    __syncthreads();                 // the previous task's readers are done with every stage
+    if (tid < a.n_stages) P.done[tid] = 0;
+    if (tid < 32)
+        for (int s = 0; s < a.n_stages && s < nst; ++s) issue(s, s, tree_of(s));
+    __syncthreads();
+    int buf = 0;
+    for (int st = 0; st < nst; ++st) {
+        // every warp prefetches the tree ids of the stage that will refill this buffer, so that whichever warp
+        // leaves it last can issue the copies without waiting on global memory
+        const int nxt = tree_of(st + a.n_stages);
+        mbar_wait(&P.full[buf], (P.phase >> buf) & 1u);
+        P.phase ^= (1u << buf);
+        const int nt = min(tps, (t1 - t0) - st * tps);
+        const unsigned char* base = P.bufs + (size_t)buf * P.stage_bytes;
+#pragma unroll 1
+        for (int tt = 0; tt < nt; ++tt, base += a.slot_bytes) f(base);
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) last = (atomicAdd(&P.done[buf], 1) == CR_THREADS / 32 - 1);
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {                                  // last warp out refills the stage
+            if (lane == 0) P.done[buf] = 0;
+            if (st + a.n_stages < nst) issue(st + a.n_stages, buf, nxt);
+        }
+        buf = (buf + 1 == a.n_stages) ? 0 : buf + 1;
+    }
+}
+
+// shared-memory byte offset of matrix row `row` inside a staged tree of task T
+__device__ __forceinline__ uint32_t cr_row_off(const RowTask& T, int row, uint32_t row_bytes) {
+    int slot = row - T.rstart[0];
+    if (slot < 0 || slot >= T.rcount[0]) {
+        slot = row - T.rstart[1];
+        if (slot >= 0 && slot < T.rcount[1]) slot += T.rcount[0];
+        else slot = row - T.rstart[2] + T.rcount[0] + T.rcount[1];
+    }
+    return (uint32_t)slot * row_bytes;
+}
+
+__global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const CountRowsArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ int s_task;
+    RowPipe P;
+    P.full = reinterpret_cast<uint64_t*>(smem);
+    P.done = reinterpret_cast<int*>(smem + 64);
+    P.bufs = smem + 128;
+    P.stage_bytes = (uint32_t)a.trees_per_stage * a.slot_bytes;
+    P.phase = 0;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < CR_MAX_STAGES; ++s) mbar_init(&P.full[s], 1);
+        fence_mbar_init();
+    }
+    // task space: class A runs the X tasks only, class B runs X and Y; each class in chunks of ~chunk_trees trees
+    const int mA = *a.n_class_a, mB = a.m - mA;
+    const int chA = (mA + a.chunk_trees - 1) / a.chunk_trees, chB = (mB + a.chunk_trees - 1) / a.chunk_trees;
+    const long long nA_tasks = (long long)chA * a.n_x, nB_tasks = (long long)chB * (a.n_x + a.n_y);
+    const bool sub0 = mB > 0;       // mixed input: class-A role-X hits are subtracted from slot 0 here; otherwise qs_table_finalize derives slot 0
+
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_task = atomicAdd(a.task_counter, 1);
+        __syncthreads();
+        const long long id = s_task;
+        if (id >= nA_tasks + nB_tasks) break;
+        int cls, chunk, base_task, nch, lo, len;
+        if (id < nA_tasks) { cls = 0; chunk = (int)(id / a.n_x); base_task = (int)(id % a.n_x); nch = chA; lo = 0; len = mA; }
+        else { const long long r = id - nA_tasks; cls = 1; chunk = (int)(r / (a.n_x + a.n_y)); base_task = (int)(r % (a.n_x + a.n_y)); nch = chB; lo = mA; len = mB; }
+        const int per = (len + nch - 1) / nch;                     // balanced chunks, each <= chunk_trees
+        const int t0 = lo + chunk * per, t1 = min(lo + len, t0 + per);
+        if (t0 >= t1) continue;
+        const RowTask T = a.tasks[base_task];
+        const bool cls_a = (cls == 0);
+        const uint32_t rb = a.row_bytes;
+
+        if (T.kind == ITEM_XO) {
+            const bool valid = tid < T.ne;
+            int c = 2, d = 3, j = 0;
+            if (valid) cr_decode_x(a.E.PXO, ITEM_XO, a.E.xo_diag, T.e0 + tid, a.n, a.d_begin, c, d, j);
+            int ib = 1, ia = 0;
+            if (valid) {
+                const int noff = ((c + 7) >> 3) * (((c + 7) >> 3) - 1) / 2;      // off-diagonal blocks first: j = ib(ib-1)/2 + ia, ia < ib
+                if (j < noff) {
+                    ib = (int)((1.f + sqrtf(1.f + 8.f * (float)j)) * 0.5f);
+                    while (ib * (ib - 1) / 2 > j) --ib;
+                    while ((ib + 1) * ib / 2 <= j) ++ib;
+                    ia = j - ib * (ib - 1) / 2;
+                } else ia = ib = j - noff;                                        // xo_diag: then the diagonal blocks
+            }
+            // pair (p,q) = (c,d)
+            const uint32_t rp = valid ? cr_row_off(T, c, rb) : 0u, rq = valid ? cr_row_off(T, d, rb) : 0u;
+            const uint32_t oPu = rp + ia * 16u, oQu = rq + ia * 16u, oPv = rp + ib * 16u, oQv = rq + ib * 16u;
+            XCounters x; zero(x);
+            stream_rows(a, P, T, t0, t1, [&](const unsigned char* s) {
+                step_gt_lt(x, BlockRows{lds128(s, oPu), lds128(s, oQu), lds128(s, oPv), lds128(s, oQv)});
+            });
+            if (valid) {
+                const uint64_t rcd = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int b = ib * 8 + jj;
+                    if (b >= c) continue;
+                    const uint64_t eb = (rcd + (uint64_t)b * (b - 1) / 2 + ia * 8) * 3;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        uint32_t g0, g1, l0, l1;
+                        decode(x.gt[jj][p], g0, g1);
+                        decode(x.lt[jj][p], l0, l1);
+                        if (ia * 8 + 2 * p >= b) { g0 = 0; l0 = 0; }              // diagonal block (xo_diag): only a < b
+                        if (ia * 8 + 2 * p + 1 >= b) { g1 = 0; l1 = 0; }
+                        const uint64_t e = eb + (uint64_t)(2 * p) * 3;
+                        table_red(a.table, a.cint_bytes, e + 1, g0); table_red(a.table, a.cint_bytes, e + 2, l0);
+                        table_red(a.table, a.cint_bytes, e + 4, g1); table_red(a.table, a.cint_bytes, e + 5, l1);
+                        if (cls_a && sub0) { table_red(a.table, a.cint_bytes, e, 0u - (g0 + l0)); table_red(a.table, a.cint_bytes, e + 3, 0u - (g1 + l1)); }
+                    }
+                }
+            }
+        } else if (T.kind == ITEM_XD) {
+            const bool vA = 2 * tid < T.ne, vB = 2 * tid + 1 < T.ne;
+            int cA = 2, dA = 3, jA = 0, cB = 2, dB = 3, jB = 0;
+            if (vA) cr_decode_x(a.E.PXD, ITEM_XD, a.E.xo_diag, T.e0 + 2 * tid, a.n, a.d_begin, cA, dA, jA);
+            if (vB) cr_decode_x(a.E.PXD, ITEM_XD, a.E.xo_diag, T.e0 + 2 * tid + 1, a.n, a.d_begin, cB, dB, jB);
+            const uint32_t oAp = (vA ? cr_row_off(T, cA, rb) : 0u) + jA * 16u, oAq = (vA ? cr_row_off(T, dA, rb) : 0u) + jA * 16u;
+            const uint32_t oBp = (vB ? cr_row_off(T, cB, rb) : 0u) + jB * 16u, oBq = (vB ? cr_row_off(T, dB, rb) : 0u) + jB * 16u;
+            GCounters ga, gb; zero(ga); zero(gb);
+            stream_rows(a, P, T, t0, t1, [&](const unsigned char* s) {
+                step_gt_diag(ga, lds128(s, oAp), lds128(s, oAq));
+                step_gt_diag(gb, lds128(s, oBp), lds128(s, oBq));
+            });
+            auto flush = [&](int c, int d, int blk, const GCounters& g) {
+                const int x0 = blk * 8;
+                const uint64_t rcd = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int y = x0 + jj;                          // the "v" taxon
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        uint32_t h[2];
+                        decode(g.gt[jj][p], h[0], h[1]);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int x = x0 + 2 * p + e;          // the "u" taxon: counted G(x) > G(y)
+                            if (x == y || max(x, y) >= c) continue;
+                            const int lo2 = min(x, y), hi2 = max(x, y);
+                            const uint64_t el = (rcd + (uint64_t)hi2 * (hi2 - 1) / 2 + lo2) * 3;
+                            table_red(a.table, a.cint_bytes, el + ((x < y) ? 1 : 2), h[e]);   // x<y: G(a)>G(b) slot 1;  x>y: G(b)>G(a) slot 2
+                            if (cls_a && sub0) table_red(a.table, a.cint_bytes, el, 0u - h[e]);
+                        }
+                    }
+                }
+            };
+            if (vA) flush(cA, dA, jA, ga);
+            if (vB) flush(cB, dB, jB, gb);
+        } else {   // ITEM_Y: pair (p,q) = (b,c), u = a-block, v = d-block
+            const bool vA = 2 * tid < T.ne, vB = 2 * tid + 1 < T.ne;
+            int bA = 1, cA = 2, iaA = 0, idA = 0, bB = 1, cB = 2, iaB = 0, idB = 0;
+            if (vA) cr_decode_y(a.E, T.e0 + 2 * tid, a.n, a.d_begin, bA, cA, iaA, idA);
+            if (vB) cr_decode_y(a.E, T.e0 + 2 * tid + 1, a.n, a.d_begin, bB, cB, iaB, idB);
+            const uint32_t pA = vA ? cr_row_off(T, bA, rb) : 0u, qA = vA ? cr_row_off(T, cA, rb) : 0u;
+            const uint32_t pB = vB ? cr_row_off(T, bB, rb) : 0u, qB = vB ? cr_row_off(T, cB, rb) : 0u;
+            const uint32_t oApu = pA + iaA * 16u, oAqu = qA + iaA * 16u, oApv = pA + idA * 16u, oAqv = qA + idA * 16u;
+            const uint32_t oBpu = pB + iaB * 16u, oBqu = qB + iaB * 16u, oBpv = pB + idB * 16u, oBqv = qB + idB * 16u;
+            GCounters ga, gb; zero(ga); zero(gb);
+            stream_rows(a, P, T, t0, t1, [&](const unsigned char* s) {
+                step_gt(ga, BlockRows{lds128(s, oApu), lds128(s, oAqu), lds128(s, oApv), lds128(s, oAqv)});
+                step_gt(gb, BlockRows{lds128(s, oBpu), lds128(s, oBqu), lds128(s, oBpv), lds128(s, oBqv)});
+            });
+            auto flush = [&](int b, int c, int ia, int id, const GCounters& g) {
+                const int dlo = max(c + 1, a.d_begin);
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int d = id * 8 + jj;
+                    if (d < dlo || d >= a.d_end) continue;
+                    const uint64_t eb = (binom4((uint64_t)d) + binom3((uint64_t)c) + (uint64_t)b * (b - 1) / 2 - a.rank_base + ia * 8) * 3;
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        uint32_t h0, h1;
+                        decode(g.gt[jj][p], h0, h1);
+                        const int a0 = ia * 8 + 2 * p;
+                        if (a0 < b) table_red(a.table, a.cint_bytes, eb + (uint64_t)(2 * p) * 3, h0);
+                        if (a0 + 1 < b) table_red(a.table, a.cint_bytes, eb + (uint64_t)(2 * p + 1) * 3, h1);
+                    }
+                }
+            };
+            if (vA) flush(bA, cA, iaA, idA, ga);
+            if (vB) flush(bB, cB, iaB, idB, gb);
+        }
+    }
+}
+
+// before counting: zero the table; with both tree classes present slot 0 starts at |A| (the class-A role-X hits
+// are subtracted from it by the counting kernel, so every field stays >= 0 at the end of the word arithmetic)
+template <typename CINT>
+__global__ void qs_table_init_kernel(CINT* __restrict__ table, uint64_t n_entries, const int32_t* __restrict__ n_class_a, int m) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int mA = *n_class_a;
+    const CINT s0 = (mA > 0 && mA < m) ? (CINT)mA : (CINT)0;
+    for (; i < n_entries * 3; i += stride) table[i] = (i % 3 == 0) ? s0 : (CINT)0;
+}
+
+// after counting, when EVERY tree is class A: slot 0 = |A| - slot 1 - slot 2; thread = one table entry
+template <typename CINT>
+__global__ void qs_table_finalize_kernel(CINT* __restrict__ table, uint64_t n_entries, const int32_t* __restrict__ n_class_a, int m) {
+    uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const int mA = *n_class_a;
+    if (mA != m) return;
+    for (; i < n_entries; i += stride) {
+        CINT* t = table + i * 3;
+        t[0] = (CINT)((CINT)mA - t[1] - t[2]);
+    }
+}
+
+}  // namespace qs

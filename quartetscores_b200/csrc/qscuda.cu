@@ -19,8 +19,7 @@
 #include <vector>
 
 #include "kernels/common.cuh"
-#include "kernels/count_items.cuh"
-#include "kernels/count_tiled.cuh"
+#include "kernels/count_rows.cuh"
 #include "kernels/dist.cuh"
 #include "kernels/score.cuh"
 #include "kernels/ubench.cuh"
@@ -30,7 +29,6 @@ using namespace qs;
 namespace {
 
 constexpr int kMaxHalfExact = 2048;     // integers up to 2048 are exact in fp16 (distances; the counters are integer)
-constexpr int kItemThreads = 512;
 
 struct HostRef {
     int n_nodes = 0, n_inner = 0;
@@ -59,6 +57,7 @@ struct qs_ctx {
     uint16_t* d_idepth = nullptr;
     int64_t* d_PB = nullptr;
     int64_t score_blocks = 0;
+    int score_dB = -1, score_dE = -1;
 
     // trees
     int64_t m = 0, total_nodes = 0, cap_nodes = 0, cap_trees = 0;
@@ -81,17 +80,13 @@ struct qs_ctx {
     int64_t class_cap = 0, n_class_a = 0;
     int* d_counter = nullptr;    // dynamic task / tile scheduling
 
-    // counting
-    uint32_t* d_ws = nullptr;
-    void* d_table = nullptr;
-    size_t table_elems = 0;
-    CountItem* d_items[3] = {nullptr, nullptr, nullptr};
-    int64_t n_items[3] = {0, 0, 0};
-    bool items_built = false;
-    CountTask* d_tasks = nullptr;
-    int n_tasks = 0;
-    int64_t tasks_for_m = -1;
-    __half* d_nan_tree = nullptr;
+    // counting (kernels/count_rows.cuh)
+    void* d_table = nullptr;     // QS_MODE_TABLE: this shard's table; QS_MODE_TABLE_FREE: the current slab
+    size_t table_bytes = 0;
+    RowTask* d_tasks = nullptr;  // task table of the d-range [plan_dB, plan_dE)
+    size_t tasks_cap = 0;
+    int plan_dB = -1, plan_dE = -1, plan_nx = 0, plan_ny = 0, plan_max_rows = 1;
+    int64_t* d_enum = nullptr;   // PXO | PXD | PY | CD prefix tables of the plan
     bool counted = false;
 
     // scoring
@@ -101,11 +96,6 @@ struct qs_ctx {
     bool fused_partials_valid = false;   // table-free mode: partials accumulated by qs_count
     int fused_scale = 1;
 
-    // tiled counting kernel
-    ushort4* d_tiles = nullptr;
-    int n_tiles = -1;
-    uint32_t* d_scratch = nullptr;
-    int scratch_ctas = 0;
 };
 
 namespace {
@@ -175,88 +165,12 @@ uint64_t cint_mask(int bytes) { return bytes >= 8 ? ~0ull : ((1ull << (8 * bytes
 void free_all(qs_ctx* c) {
     cudaFree(c->d_lca); cudaFree(c->d_idepth); cudaFree(c->d_PB);
     cudaFree(c->d_off); cudaFree(c->d_parent); cudaFree(c->d_leaf);
-    cudaFree(c->d_D); cudaFree(c->d_flags); cudaFree(c->d_ws); cudaFree(c->d_table);
+    cudaFree(c->d_D); cudaFree(c->d_flags); cudaFree(c->d_table);
     cudaFree(c->d_class); cudaFree(c->d_order); cudaFree(c->d_nA); cudaFree(c->d_counter);
-    for (auto& p : c->d_items) cudaFree(p);
-    cudaFree(c->d_tasks); cudaFree(c->d_nan_tree);
-    cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best); cudaFree(c->d_tiles); cudaFree(c->d_scratch);
+    cudaFree(c->d_tasks); cudaFree(c->d_enum);
+    cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
-}
-
-// does the whole-matrix kernel apply?  two pipeline stages of one tree pair each must fit in shared memory
-bool small_path_ok(const qs_ctx* c) {
-    size_t tree_bytes = (size_t)c->n * c->n_pad * 2;
-    return 256 + 4 * tree_bytes <= (size_t)c->smem_optin;
-}
-
-// ---- work items of the whole-matrix counting kernel (see kernels/count_items.cuh) ------------------
-int build_items(qs_ctx* c) {
-    const int n = c->n, dB = c->d_begin, dE = c->d_end;
-    std::vector<CountItem> xo, xd, y;
-    for (int cc = 2; cc < n - 1; ++cc) {
-        const int nb = (cc + 7) / 8;                       // blocks holding some b < c
-        for (int d = std::max(cc + 1, dB); d < dE; ++d) {
-            for (int ib = 0; ib < nb; ++ib) {
-                for (int ia = 0; ia < ib; ++ia) xo.push_back(CountItem{(uint16_t)cc, (uint16_t)d, (uint16_t)ia, (uint16_t)ib});
-                if (ib * 8 + 1 < cc) xd.push_back(CountItem{(uint16_t)cc, (uint16_t)d, (uint16_t)ib, (uint16_t)ib});
-            }
-        }
-    }
-    for (int b = 1; b < n - 2; ++b) {
-        const int na = (b + 7) / 8;
-        for (int cc = b + 1; cc < n - 1; ++cc) {
-            const int dlo = std::max(cc + 1, dB);
-            if (dlo >= dE) continue;
-            for (int id = dlo / 8; id <= (dE - 1) / 8; ++id)
-                for (int ia = 0; ia < na; ++ia) y.push_back(CountItem{(uint16_t)b, (uint16_t)cc, (uint16_t)ia, (uint16_t)id});
-        }
-    }
-    const std::vector<CountItem>* lists[3] = {&xo, &xd, &y};
-    for (int k = 0; k < 3; ++k) {
-        if (lists[k]->size() > 0x7fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "item count overflow");
-        c->n_items[k] = (int64_t)lists[k]->size();
-        int r;
-        if ((r = dev_alloc(c, &c->d_items[k], lists[k]->size()))) return r;
-        if (!lists[k]->empty()) QS_CUDA(c, cudaMemcpy(c->d_items[k], lists[k]->data(), lists[k]->size() * sizeof(CountItem), cudaMemcpyHostToDevice));
-    }
-    c->items_built = true;
-    return QS_OK;
-}
-
-// tasks = (kind, block of thread-items, tree class, chunk of that class); the class sizes are only known
-// on the device, so every class gets the same number of chunks and empty tasks return at once
-int build_tasks(qs_ctx* c) {
-    const int per_task[3] = {kItemThreads, 2 * kItemThreads, 2 * kItemThreads};
-    int64_t blocks[3], total_blocks = 0;
-    for (int k = 0; k < 3; ++k) { blocks[k] = (c->n_items[k] + per_task[k] - 1) / per_task[k]; total_blocks += blocks[k]; }
-    int nchunks = (int)((c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES);
-    // enough tasks for the dynamic scheduler to balance (~8 per SM), but chunks of at least 256 trees
-    while ((int64_t)nchunks * total_blocks < 8LL * c->num_sms && c->m / (nchunks + 1) >= 256) ++nchunks;
-    std::vector<CountTask> tasks;
-    for (int chunk = 0; chunk < nchunks; ++chunk)
-        for (int k = 0; k < 3; ++k)
-            for (int64_t b = 0; b < blocks[k]; ++b) {
-                const int32_t first = (int32_t)(b * per_task[k]);
-                const int32_t count = (int32_t)std::min<int64_t>(per_task[k], c->n_items[k] - first);
-                if (k != ITEM_Y) tasks.push_back(CountTask{k, first, count, 0, chunk, nchunks});
-                tasks.push_back(CountTask{k, first, count, 1, chunk, nchunks});
-            }
-    if (tasks.size() > 0x7fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
-    int r;
-    if ((r = dev_alloc(c, &c->d_tasks, tasks.size()))) return r;
-    if (!tasks.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks, tasks.data(), tasks.size() * sizeof(CountTask), cudaMemcpyHostToDevice));
-    c->n_tasks = (int)tasks.size();
-    c->tasks_for_m = c->m;
-    return QS_OK;
-}
-
-template <typename CINT>
-void launch_narrow(qs_ctx* c, uint64_t elems) {
-    int blocks = (int)std::min<uint64_t>((elems + 255) / 256, (uint64_t)c->num_sms * 16);
-    if (blocks < 1) blocks = 1;
-    qs_narrow_kernel<CINT><<<blocks, 256, 0, c->stream>>>(c->d_ws, (CINT*)c->d_table, elems, c->d_nA);
-    c->launches++;
 }
 
 template <typename CINT>
@@ -299,134 +213,193 @@ int run_distances(qs_ctx* c) {
     return QS_OK;
 }
 
-int run_count_items(qs_ctx* c) {
-    int r;
-    if (!c->items_built && (r = build_items(c))) return r;
-    if (c->tasks_for_m != c->m && (r = build_tasks(c))) return r;
-    const uint64_t nq = c->rank_end - c->rank_begin;
-    if (!c->d_ws && (r = dev_alloc(c, &c->d_ws, (size_t)nq * QS_WS_SLOTS))) return r;
-    const uint32_t tree_bytes = (uint32_t)((size_t)c->n * c->n_pad * 2);
-    if (!c->d_nan_tree) {
-        if ((r = dev_alloc(c, &c->d_nan_tree, (size_t)tree_bytes / 2))) return r;
-        QS_CUDA(c, cudaMemsetAsync(c->d_nan_tree, 0xFF, tree_bytes, c->stream));
+// ---- task table of the counting kernel for the quartets with d in [dB, dE) (see kernels/count_rows.cuh) ----
+struct HostEnum {
+    std::vector<int64_t> PXO, PXD, PY, CD;
+    int xo_diag = 0;
+    EnumTables view() const { return EnumTables{PXO.data(), PXD.data(), PY.data(), CD.data(), xo_diag}; }
+};
+
+// separate half-cost tasks for the diagonal blocks pay off while a task's rows can cover most of the matrix
+int use_xo_diag(int n) { return n > 160 ? 1 : 0; }
+
+void build_enum_tables(int n, int dB, int dE, HostEnum& H) {
+    H.xo_diag = use_xo_diag(n);
+    H.PXO.assign(n + 1, 0); H.PXD.assign(n + 1, 0); H.PY.assign(n + 1, 0); H.CD.assign(n + 1, 0);
+    for (int c = 0; c < n; ++c) {
+        const int64_t nd = (c >= 2) ? std::max(0, dE - cr_dlo(c, dB)) : 0;
+        H.PXO[c + 1] = H.PXO[c] + nd * cr_nxo(c, H.xo_diag);
+        H.PXD[c + 1] = H.PXD[c] + nd * cr_nxd(c, H.xo_diag);
+        H.CD[c + 1] = H.CD[c] + ((c >= 2) ? cr_ndb(c, dB, dE) : 0);
     }
-    QS_CUDA(c, cudaMemsetAsync(c->d_ws, 0, (size_t)nq * QS_WS_SLOTS * sizeof(uint32_t), c->stream));
-    QS_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
-    if (c->n_tasks == 0) return QS_OK;
-    CountItemsArgs a;
-    a.D = c->d_D; a.order = c->d_order; a.n_class_a = c->d_nA; a.nan_tree = c->d_nan_tree;
-    for (int k = 0; k < 3; ++k) a.items[k] = c->d_items[k];
-    a.tasks = c->d_tasks; a.n_tasks = c->n_tasks; a.task_counter = c->d_counter;
-    a.ws = c->d_ws; a.rank_base = c->rank_begin; a.n = c->n; a.n_pad = c->n_pad; a.m = (int)c->m;
-    a.d_begin = c->d_begin; a.d_end = c->d_end; a.tree_bytes = tree_bytes;
-    a.n_stages = (int)std::min<size_t>(CI_MAX_STAGES, ((size_t)c->smem_optin - 256) / (2 * (size_t)tree_bytes));
-    const size_t smem = 128 + (size_t)a.n_stages * 2 * tree_bytes;
-    QS_CUDA(c, cudaFuncSetAttribute(qs_count_items_kernel<kItemThreads>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = std::min(c->n_tasks, c->num_sms);
-    QS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));       // count_ms brackets the counting kernel alone
-    qs_count_items_kernel<kItemThreads><<<grid, kItemThreads, smem, c->stream>>>(a);
-    QS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
-    c->launches++;
-    QS_CUDA(c, cudaGetLastError());
-    // workspace -> CINT table
-    switch (c->cint_bytes) {
-        case 1: launch_narrow<uint8_t>(c, nq); break;
-        case 2: launch_narrow<uint16_t>(c, nq); break;
-        case 4: launch_narrow<uint32_t>(c, nq); break;
-        default: launch_narrow<unsigned long long>(c, nq); break;
+    for (int b = 0; b < n; ++b) {
+        int64_t items = 0;
+        if (b >= 1 && b + 1 < n) items = (int64_t)((b + 7) / 8) * (H.CD[n] - H.CD[b + 1]);
+        H.PY[b + 1] = H.PY[b] + items;
     }
-    QS_CUDA(c, cudaGetLastError());
-    return QS_OK;
 }
 
-// ---- tiled counting kernel (kernels/count_tiled.cuh) ---------------------------------------------
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_dist_tensor_map(qs_ctx* c, CUtensorMap* tm, int box_rows, int box_cols) {
-    static PFN_encodeTiled encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        QS_CUDA(c, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-        if (!fn || qres != cudaDriverEntryPointSuccess) QS_FAIL(c, QS_E_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
-        encode = (PFN_encodeTiled)fn;
+// rows touched by the items [e0, e0+ne) of one kind, as sorted disjoint intervals [lo, hi]
+void task_row_intervals(const HostEnum& H, int kind, int64_t e0, int ne, int n, int dB, int dE, std::vector<std::pair<int, int>>& iv) {
+    iv.clear();
+    int p0, q0, p1, q1, t0, t1;
+    if (kind == ITEM_Y) {
+        cr_decode_y(H.view(), e0, n, dB, p0, q0, t0, t1);
+        cr_decode_y(H.view(), e0 + ne - 1, n, dB, p1, q1, t0, t1);
+    } else {
+        const int64_t* P = kind == ITEM_XO ? H.PXO.data() : H.PXD.data();
+        cr_decode_x(P, kind, H.xo_diag, e0, n, dB, p0, q0, t0);
+        cr_decode_x(P, kind, H.xo_diag, e0 + ne - 1, n, dB, p1, q1, t0);
     }
-    const cuuint64_t gdim[3] = {(cuuint64_t)c->n_pad, (cuuint64_t)c->n, (cuuint64_t)c->m};
-    const cuuint64_t gstride[2] = {(cuuint64_t)c->n_pad * 2, (cuuint64_t)c->n * c->n_pad * 2};
-    const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
-    const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, (void*)c->d_D, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) QS_FAIL(c, QS_E_CUDA, "cuTensorMapEncodeTiled failed with %d", (int)r);
-    return QS_OK;
+    // outer (fixed) rows p0..p1; inner (variable) rows: tail of p0, everything of the rows in between, head of p1
+    const int qmax = (kind == ITEM_Y) ? dE - 2 : dE - 1;                 // last inner row that has items
+    auto qlo = [&](int p) { return (kind == ITEM_Y) ? p + 1 : cr_dlo(p, dB); };
+    iv.emplace_back(p0, p1);
+    if (p0 == p1) iv.emplace_back(q0, q1);
+    else {
+        iv.emplace_back(q0, qmax);
+        if (p1 - p0 >= 2) iv.emplace_back(qlo(p0 + 1), qmax);
+        iv.emplace_back(qlo(p1), q1);
+    }
+    std::sort(iv.begin(), iv.end());
+    std::vector<std::pair<int, int>> m;
+    for (auto& x : iv) {
+        if (x.second < x.first) continue;
+        if (!m.empty() && x.first <= m.back().second + 1) m.back().second = std::max(m.back().second, x.second);
+        else m.push_back(x);
+    }
+    while (m.size() > 3) {                                               // close the smallest gap
+        size_t best = 0; int gap = 1 << 30;
+        for (size_t i = 0; i + 1 < m.size(); ++i) if (m[i + 1].first - m[i].second < gap) { gap = m[i + 1].first - m[i].second; best = i; }
+        m[best].second = m[best + 1].second;
+        m.erase(m.begin() + best + 1);
+    }
+    iv.swap(m);
 }
 
-int build_tiles(qs_ctx* c) {
-    std::vector<ushort4> tiles;
-    const int dlo = std::max(3, c->d_begin), dhi = c->d_end;       // d in [dlo, dhi); d-tiles are anchored at dlo
-    for (int jd = 0; dlo + jd * 8 < dhi; ++jd) {
-        const int d_max = std::min(dlo + jd * 8 + 7, dhi - 1);
-        for (int ic = 0; ic * 16 <= d_max - 1; ++ic) {
-            const int c_max = std::min(ic * 16 + 15, d_max - 1);
-            if (c_max < 2) continue;
-            for (int ib = 0; ib * 16 <= c_max - 1; ++ib) {
-                const int b_max = std::min(ib * 16 + 15, c_max - 1);
-                if (b_max < 1) continue;
-                for (int ia = 0; ia * 16 <= b_max - 1; ++ia) tiles.push_back(make_ushort4((unsigned short)ia, (unsigned short)ib, (unsigned short)ic, (unsigned short)jd));
+void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, std::vector<RowTask>& xt, std::vector<RowTask>& yt) {
+    xt.clear(); yt.clear();
+    std::vector<std::pair<int, int>> iv;
+    auto rows_of = [&](const std::vector<std::pair<int, int>>& v) { int r = 0; for (auto& x : v) r += x.second - x.first + 1; return r; };
+    auto emit = [&](std::vector<RowTask>& out, int kind, int64_t total, int cap) {
+        int64_t e = 0;
+        while (e < total) {
+            int ne = (int)std::min<int64_t>(cap, total - e);
+            task_row_intervals(H, kind, e, ne, n, dB, dE, iv);
+            while (rows_of(iv) > max_rows && ne > 1) {                   // shrink until the rows fit the shared-memory slot
+                ne = std::max(1, ne / 2);
+                task_row_intervals(H, kind, e, ne, n, dB, dE, iv);
             }
+            RowTask t{};
+            t.kind = kind; t.ne = ne; t.e0 = e;
+            for (size_t k = 0; k < 3; ++k) { t.rstart[k] = k < iv.size() ? iv[k].first : 0; t.rcount[k] = k < iv.size() ? iv[k].second - iv[k].first + 1 : 0; }
+            out.push_back(t);
+            e += ne;
         }
-    }
-    if (tiles.size() > 0x7fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "too many tiles");
-    c->n_tiles = (int)tiles.size();
+    };
+    emit(xt, ITEM_XO, H.PXO[n], CR_THREADS);
+    emit(xt, ITEM_XD, H.PXD[n], 2 * CR_THREADS);
+    emit(yt, ITEM_Y, H.PY[n], 2 * CR_THREADS);
+}
+
+int ensure_plan(qs_ctx* c, int dB, int dE) {
+    if (c->plan_dB == dB && c->plan_dE == dE) return QS_OK;
+    const size_t row_bytes = (size_t)c->n_pad * 2;
+    // shared-memory budget per staged tree: ~24 KB (the whole matrix when n <= ~110), at least 4 rows
+    const int max_rows = (int)std::max<size_t>(4, std::min<size_t>((size_t)c->n, (24 * 1024) / row_bytes));
+    if ((size_t)max_rows * row_bytes * 2 + 256 > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: matrix rows of %zu bytes are too long for the counting kernel's shared-memory pipeline", c->n, row_bytes);
+    HostEnum H;
+    build_enum_tables(c->n, dB, dE, H);
+    std::vector<RowTask> xt, yt;
+    build_row_tasks(H, c->n, dB, dE, max_rows, xt, yt);
+    if (xt.size() + yt.size() > 0x3fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
+    int mx = 1;
+    for (auto* v : {&xt, &yt}) for (auto& t : *v) mx = std::max(mx, t.rcount[0] + t.rcount[1] + t.rcount[2]);
+    const size_t total = xt.size() + yt.size();
     int r;
-    if ((r = dev_alloc(c, &c->d_tiles, tiles.size()))) return r;
-    if (!tiles.empty()) QS_CUDA(c, cudaMemcpy(c->d_tiles, tiles.data(), tiles.size() * sizeof(ushort4), cudaMemcpyHostToDevice));
+    if (total > c->tasks_cap) {
+        if ((r = dev_alloc(c, &c->d_tasks, total + total / 4))) { c->tasks_cap = 0; return r; }
+        c->tasks_cap = total + total / 4;
+    }
+    if (!c->d_enum && (r = dev_alloc(c, &c->d_enum, (size_t)4 * (c->n + 1)))) return r;
+    QS_CUDA(c, cudaStreamSynchronize(c->stream));      // a running kernel may still read the previous tables
+    if (!xt.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks, xt.data(), xt.size() * sizeof(RowTask), cudaMemcpyHostToDevice));
+    if (!yt.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks + xt.size(), yt.data(), yt.size() * sizeof(RowTask), cudaMemcpyHostToDevice));
+    const size_t np1 = (size_t)c->n + 1;
+    QS_CUDA(c, cudaMemcpy(c->d_enum, H.PXO.data(), np1 * 8, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_enum + np1, H.PXD.data(), np1 * 8, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_enum + 2 * np1, H.PY.data(), np1 * 8, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_enum + 3 * np1, H.CD.data(), np1 * 8, cudaMemcpyHostToDevice));
+    c->plan_dB = dB; c->plan_dE = dE; c->plan_nx = (int)xt.size(); c->plan_ny = (int)yt.size(); c->plan_max_rows = mx;
     return QS_OK;
 }
 
-int ensure_pair_arrays(qs_ctx* c);
+template <typename CINT>
+void launch_init(qs_ctx* c, void* table, uint64_t n_entries) {
+    int blocks = (int)std::min<uint64_t>((n_entries * 3 + 255) / 256, (uint64_t)c->num_sms * 16);
+    if (blocks < 1) blocks = 1;
+    qs_table_init_kernel<CINT><<<blocks, 256, 0, c->stream>>>((CINT*)table, n_entries, c->d_nA, (int)c->m);
+    c->launches++;
+}
 
-int run_count_tiled(qs_ctx* c) {
+template <typename CINT>
+void launch_finalize(qs_ctx* c, void* table, uint64_t n_entries) {
+    int blocks = (int)std::min<uint64_t>((n_entries + 255) / 256, (uint64_t)c->num_sms * 16);
+    if (blocks < 1) blocks = 1;
+    qs_table_finalize_kernel<CINT><<<blocks, 256, 0, c->stream>>>((CINT*)table, n_entries, c->d_nA, (int)c->m);
+    c->launches++;
+}
+
+// count the quartets with d in [dB, dE) into `table` (rank_base = C(dB,4)); the distance matrices must be built
+int run_count_rows(qs_ctx* c, int dB, int dE, void* table) {
+    const uint64_t rb = binom4((uint64_t)dB), re = binom4((uint64_t)dE);
+    const uint64_t nq = re - rb;
+    if (nq == 0) return QS_OK;
     int r;
-    if (c->n_tiles < 0 && (r = build_tiles(c))) return r;
-    if (c->n_tiles == 0) return QS_OK;
-    const int grid = std::min(c->n_tiles, c->num_sms);
-    if (c->scratch_ctas < grid) {
-        if ((r = dev_alloc(c, &c->d_scratch, (size_t)grid * CT_TILE_Q * 3))) { c->scratch_ctas = 0; return r; }
-        c->scratch_ctas = grid;
+    if ((r = ensure_plan(c, dB, dE))) return r;
+    switch (c->cint_bytes) {
+        case 1: launch_init<uint8_t>(c, table, nq); break;
+        case 2: launch_init<uint16_t>(c, table, nq); break;
+        case 4: launch_init<uint32_t>(c, table, nq); break;
+        default: launch_init<unsigned long long>(c, table, nq); break;
     }
-    CUtensorMap tm16x16, tm8x16, tm16x8;
-    if ((r = make_dist_tensor_map(c, &tm16x16, 16, 16))) return r;
-    if ((r = make_dist_tensor_map(c, &tm8x16, 8, 16))) return r;
-    if ((r = make_dist_tensor_map(c, &tm16x8, 16, 8))) return r;
-    CountTiledArgs a;
-    memset(&a, 0, sizeof(a));
-    a.tiles = c->d_tiles; a.n_tiles = c->n_tiles; a.n = c->n; a.m = (int)c->m; a.d_begin = c->d_begin; a.d_end = c->d_end;
-    a.order = c->d_order; a.n_class_a = c->d_nA; a.tile_counter = c->d_counter; a.d_tile_base = std::max(3, c->d_begin);
     QS_CUDA(c, cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->stream));
-    a.rank_base = c->rank_begin; a.scratch = c->d_scratch; a.cint_bytes = c->cint_bytes;
-    a.table = (c->mode == QS_MODE_TABLE) ? c->d_table : nullptr;
-    a.fused_score = (c->mode == QS_MODE_TABLE_FREE) ? 1 : 0;
-    if (a.fused_score) {
-        if (!c->has_ref) QS_FAIL(c, QS_E_STATE, "a table-free context scores while it counts: call qs_set_reference before qs_count");
-        if ((r = ensure_pair_arrays(c))) return r;
-        const size_t I = c->ref.n_inner;
-        QS_CUDA(c, cudaMemsetAsync(c->d_pair_sums, 0, I * I * 3 * 8, c->stream));
-        QS_CUDA(c, cudaMemsetAsync(c->d_pair_best, 0xFF, I * I * 8, c->stream));
-        ScoreArgs& sa = a.sa;
-        sa.table = nullptr; sa.rank_base = c->rank_begin; sa.lca = c->d_lca; sa.idepth = c->d_idepth; sa.pair_sums = c->d_pair_sums;
-        sa.pair_best = c->d_pair_best; sa.PB = nullptr; sa.n = c->n; sa.I = (int)I; sa.d_begin = c->d_begin; sa.d_end = c->d_end;
-        sa.count_scale = c->fused_scale; sa.cint_mask = cint_mask(c->cint_bytes); sa.bifurcating = c->ref.bifurcating ? 1 : 0;
-    }
-    const size_t smem = 128 + (size_t)CT_STAGES * CT_STAGE_BYTES;
-    QS_CUDA(c, cudaFuncSetAttribute(qs_count_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    QS_CUDA(c, cudaEventRecord(c->ev[2], c->stream));
-    qs_count_tiled_kernel<<<grid, CT_THREADS, smem, c->stream>>>(a, tm16x16, tm8x16, tm16x8);
-    QS_CUDA(c, cudaEventRecord(c->ev[3], c->stream));
+    CountRowsArgs a;
+    a.D = c->d_D; a.order = c->d_order; a.n_class_a = c->d_nA;
+    a.tasks = c->d_tasks; a.n_x = c->plan_nx; a.n_y = c->plan_ny;
+    const size_t np1 = (size_t)c->n + 1;
+    a.E = EnumTables{c->d_enum, c->d_enum + np1, c->d_enum + 2 * np1, c->d_enum + 3 * np1, use_xo_diag(c->n)};
+    a.task_counter = c->d_counter; a.table = table; a.cint_bytes = c->cint_bytes; a.rank_base = rb;
+    a.n = c->n; a.n_pad = c->n_pad; a.m = (int)c->m; a.d_begin = dB; a.d_end = dE;
+    a.row_bytes = (uint32_t)c->n_pad * 2u;
+    a.slot_bytes = (uint32_t)c->plan_max_rows * a.row_bytes;
+    // pipeline: trees_per_stage x n_stages slots of slot_bytes
+    const size_t budget = (size_t)c->smem_optin - 256;
+    int tps = CR_MAX_TPS;
+    while (tps > 1 && (size_t)2 * tps * a.slot_bytes > budget) --tps;
+    int nst = (int)std::min<size_t>(CR_MAX_STAGES, budget / ((size_t)tps * a.slot_bytes));
+    if (nst < 2) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: two pipeline stages of %u-byte row slots do not fit in shared memory", c->n, a.slot_bytes);
+    a.trees_per_stage = tps; a.n_stages = nst;
+    // tree chunks: <= 4096 trees (fp16 counters), and enough tasks for the dynamic scheduler to balance (~8 per SM)
+    const int64_t base = std::max<int64_t>(1, (int64_t)a.n_x + a.n_y);
+    int64_t want_chunks = std::max<int64_t>(1, (8LL * c->num_sms + base - 1) / base);
+    int64_t chunk = std::max<int64_t>(256, (c->m + want_chunks - 1) / want_chunks);
+    a.chunk_trees = (int)std::min<int64_t>(QS_MAX_CHUNK_TREES, chunk);
+    const size_t smem = 128 + (size_t)nst * tps * a.slot_bytes;
+    QS_CUDA(c, cudaFuncSetAttribute(qs_count_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int64_t max_tasks = base * 2 * ((c->m + a.chunk_trees - 1) / a.chunk_trees + 1);
+    if (max_tasks > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
+    const int grid = (int)std::min<int64_t>(max_tasks, c->num_sms);
+    qs_count_rows_kernel<<<grid, CR_THREADS, smem, c->stream>>>(a);
     c->launches++;
     QS_CUDA(c, cudaGetLastError());
-    if (a.fused_score) c->fused_partials_valid = true;
+    switch (c->cint_bytes) {
+        case 1: launch_finalize<uint8_t>(c, table, nq); break;
+        case 2: launch_finalize<uint16_t>(c, table, nq); break;
+        case 4: launch_finalize<uint32_t>(c, table, nq); break;
+        default: launch_finalize<unsigned long long>(c, table, nq); break;
+    }
+    QS_CUDA(c, cudaGetLastError());
     return QS_OK;
 }
 
@@ -510,17 +483,18 @@ int build_reference(qs_ctx* c, int n_nodes, const int32_t* parent, const int32_t
     return QS_OK;
 }
 
-// per-b block prefix of the table scan (kernels/score.cuh): thread = (c,d) pair, d in the shard range
-int build_score_blocks(qs_ctx* c) {
+// per-b block prefix of the table scan (kernels/score.cuh): thread = (c,d) pair, d in [dB, dE)
+int build_score_blocks(qs_ctx* c, int dB, int dE) {
+    if (c->score_dB == dB && c->score_dE == dE && c->d_PB) return QS_OK;
     const int n = c->n;
     std::vector<int64_t> PB(n + 1, 0);
     int64_t acc = 0;
     for (int b = 0; b < n; ++b) {
         PB[b] = acc;
         if (b >= 1 && b <= n - 3) {
-            int dlo = std::max(b + 2, c->d_begin);
-            if (dlo < c->d_end) {
-                int64_t k0 = dlo - b - 1, k1 = c->d_end - b - 1;       // pairs = sum_{k=k0}^{k1-1} k
+            int dlo = std::max(b + 2, dB);
+            if (dlo < dE) {
+                int64_t k0 = dlo - b - 1, k1 = dE - b - 1;       // pairs = sum_{k=k0}^{k1-1} k
                 int64_t pairs = k1 * (k1 - 1) / 2 - k0 * (k0 - 1) / 2;
                 acc += (pairs + 127) / 128;
             }
@@ -530,8 +504,10 @@ int build_score_blocks(qs_ctx* c) {
     c->score_blocks = acc;
     if (acc > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "score grid too large");
     int r;
-    if ((r = dev_alloc(c, &c->d_PB, n + 1))) return r;
+    if (!c->d_PB && (r = dev_alloc(c, &c->d_PB, n + 1))) return r;
+    QS_CUDA(c, cudaStreamSynchronize(c->stream));
     QS_CUDA(c, cudaMemcpy(c->d_PB, PB.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
+    c->score_dB = dB; c->score_dE = dE;
     return QS_OK;
 }
 
@@ -543,7 +519,67 @@ int ensure_pair_arrays(qs_ctx* c) {
     return QS_OK;
 }
 
-// scan the resident table on the device -> per-pair partials on the host
+int clear_pair_arrays(qs_ctx* c) {
+    const size_t I = c->ref.n_inner;
+    QS_CUDA(c, cudaMemsetAsync(c->d_pair_sums, 0, I * I * 3 * 8, c->stream));
+    QS_CUDA(c, cudaMemsetAsync(c->d_pair_best, 0xFF, I * I * 8, c->stream));
+    return QS_OK;
+}
+
+// scan a table holding the quartets with d in [dB, dE) and accumulate into the per-pair partials on the device
+int scan_table(qs_ctx* c, const void* table, int dB, int dE, int count_scale) {
+    int r;
+    if ((r = build_score_blocks(c, dB, dE))) return r;
+    if (c->score_blocks == 0) return QS_OK;
+    ScoreArgs a;
+    a.table = table; a.rank_base = binom4((uint64_t)dB); a.lca = c->d_lca; a.idepth = c->d_idepth;
+    a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.PB = c->d_PB; a.n = c->n; a.I = c->ref.n_inner;
+    a.d_begin = dB; a.d_end = dE; a.count_scale = count_scale; a.cint_mask = cint_mask(c->cint_bytes);
+    a.bifurcating = c->ref.bifurcating ? 1 : 0;
+    switch (c->cint_bytes) {
+        case 1: launch_score<uint8_t>(c, a); break;
+        case 2: launch_score<uint16_t>(c, a); break;
+        case 4: launch_score<uint32_t>(c, a); break;
+        default: launch_score<unsigned long long>(c, a); break;
+    }
+    QS_CUDA(c, cudaGetLastError());
+    return QS_OK;
+}
+
+// QS_MODE_TABLE_FREE (the -s analogue): the shard's d-range is processed in slabs that fit the device; each slab is
+// counted into a temporary table, scanned into the per-pair partials and discarded
+int run_table_free(qs_ctx* c) {
+    if (!c->has_ref) QS_FAIL(c, QS_E_STATE, "a table-free context scores while it counts: call qs_set_reference before qs_count");
+    int r;
+    if ((r = ensure_pair_arrays(c))) return r;
+    if ((r = clear_pair_arrays(c))) return r;
+    size_t free_b = 0, total_b = 0;
+    QS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+    size_t budget = (free_b + c->table_bytes) / 10 * 6;                 // leave room for the distance matrices of a later, larger run
+    if (const char* env = getenv("QS_SLAB_BYTES")) budget = (size_t)strtoull(env, nullptr, 10);   // test hook: force several slabs
+    const size_t eb = 3 * (size_t)c->cint_bytes;
+    int dB = std::max(3, c->d_begin);
+    while (dB < c->d_end) {
+        // largest dE (8-aligned when possible, so that role Y's d-blocks are full) whose slab fits the budget
+        int dE = dB + 1;
+        while (dE < c->d_end && (binom4((uint64_t)dE + 1) - binom4((uint64_t)dB)) * eb <= budget) ++dE;
+        if (dE < c->d_end && dE - dB > 8) dE = std::max(dB + 1, dE & ~7);
+        const size_t need = (size_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB)) * eb;
+        if (need > c->table_bytes) {
+            if (c->d_table) { cudaFree(c->d_table); c->d_table = nullptr; c->table_bytes = 0; }
+            cudaError_t e = cudaMalloc(&c->d_table, need);
+            if (e != cudaSuccess) { cudaGetLastError(); QS_FAIL(c, QS_E_MEMORY, "Insufficient memory! a slab of %zu bytes (d in [%d,%d)) does not fit this device", need, dB, dE); }
+            c->table_bytes = need;
+        }
+        if ((r = run_count_rows(c, dB, dE, c->d_table))) return r;
+        if ((r = scan_table(c, c->d_table, dB, dE, c->fused_scale))) return r;
+        dB = dE;
+    }
+    c->fused_partials_valid = true;
+    return QS_OK;
+}
+
+// QS_MODE_TABLE: scan the resident table; both modes: per-pair partials -> host
 int run_score_scan(qs_ctx* c, int count_scale) {
     if (!c->has_ref) QS_FAIL(c, QS_E_STATE, "qs_set_reference has not been called");
     if (!c->counted) QS_FAIL(c, QS_E_STATE, "qs_count has not been called");
@@ -555,24 +591,10 @@ int run_score_scan(qs_ctx* c, int count_scale) {
             QS_FAIL(c, QS_E_STATE, "table-free context: partials were accumulated by qs_count with count_scale=%d", c->fused_scale);
     } else {
         if ((r = ensure_pair_arrays(c))) return r;
-        if (!c->d_PB && (r = build_score_blocks(c))) return r;
+        if ((r = build_score_blocks(c, c->d_begin, c->d_end))) return r;
         QS_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
-        QS_CUDA(c, cudaMemsetAsync(c->d_pair_sums, 0, I * I * 3 * 8, c->stream));
-        QS_CUDA(c, cudaMemsetAsync(c->d_pair_best, 0xFF, I * I * 8, c->stream));
-        if (c->score_blocks > 0) {
-            ScoreArgs a;
-            a.table = c->d_table; a.rank_base = c->rank_begin; a.lca = c->d_lca; a.idepth = c->d_idepth;
-            a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.PB = c->d_PB; a.n = c->n; a.I = (int)I;
-            a.d_begin = c->d_begin; a.d_end = c->d_end; a.count_scale = count_scale; a.cint_mask = cint_mask(c->cint_bytes);
-            a.bifurcating = c->ref.bifurcating ? 1 : 0;
-            switch (c->cint_bytes) {
-                case 1: launch_score<uint8_t>(c, a); break;
-                case 2: launch_score<uint16_t>(c, a); break;
-                case 4: launch_score<uint32_t>(c, a); break;
-                default: launch_score<unsigned long long>(c, a); break;
-            }
-            QS_CUDA(c, cudaGetLastError());
-        }
+        if ((r = clear_pair_arrays(c))) return r;
+        if ((r = scan_table(c, c->d_table, c->d_begin, c->d_end, count_scale))) return r;
         QS_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
     }
     c->h_pair_sums.resize(I * I * 3);
@@ -739,6 +761,7 @@ int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int3
     QS_CUDA(ctx, cudaMemcpy(ctx->d_idepth, ctx->ref.idepth.data(), (size_t)ctx->ref.n_inner * 2, cudaMemcpyHostToDevice));
     if (ctx->d_pair_sums) { cudaFree(ctx->d_pair_sums); ctx->d_pair_sums = nullptr; }
     if (ctx->d_pair_best) { cudaFree(ctx->d_pair_best); ctx->d_pair_best = nullptr; }
+    ctx->score_dB = ctx->score_dE = -1;
     ctx->fused_partials_valid = false;
     ctx->has_ref = true;
     return QS_OK;
@@ -822,24 +845,20 @@ int qs_count(qs_ctx* ctx) {
     if ((r = run_distances(ctx))) return r;
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
     const uint64_t nq = ctx->rank_end - ctx->rank_begin;
-    if (ctx->mode == QS_MODE_TABLE) {
-        if (ctx->table_elems != nq * 3 || !ctx->d_table) {
-            if (ctx->d_table) { cudaFree(ctx->d_table); ctx->d_table = nullptr; }
-            if (nq) {
-                cudaError_t e = cudaMalloc(&ctx->d_table, (size_t)nq * 3 * ctx->cint_bytes);
-                if (e != cudaSuccess) { cudaGetLastError(); QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! count table of %llu bytes does not fit this device", (unsigned long long)(nq * 3 * ctx->cint_bytes)); }
-            }
-            ctx->table_elems = nq * 3;
-        }
-    }
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    QS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    if (nq) {
-        const char* force = getenv("QS_FORCE_TILED");      // test hook: exercise the tiled kernel on small inputs
-        if (ctx->mode == QS_MODE_TABLE && small_path_ok(ctx) && !(force && force[0] == '1')) r = run_count_items(ctx);
-        else r = run_count_tiled(ctx);
-        if (r) return r;
+    if (ctx->mode == QS_MODE_TABLE) {
+        const size_t need = (size_t)nq * 3 * ctx->cint_bytes;
+        if (need > ctx->table_bytes) {
+            if (ctx->d_table) { cudaFree(ctx->d_table); ctx->d_table = nullptr; ctx->table_bytes = 0; }
+            cudaError_t e = cudaMalloc(&ctx->d_table, need);
+            if (e != cudaSuccess) { cudaGetLastError(); QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! count table of %zu bytes does not fit this device (use QS_MODE_TABLE_FREE or more shards)", need); }
+            ctx->table_bytes = need;
+        }
+        if ((r = run_count_rows(ctx, ctx->d_begin, ctx->d_end, ctx->d_table))) return r;
+    } else {
+        if ((r = run_table_free(ctx))) return r;
     }
+    QS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
     int flags[2] = {0, 0};
     int32_t nA = 0;
     QS_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
@@ -901,6 +920,51 @@ int qs_shard_bounds(int n_taxa, int shard_index, int shard_count, int* s3_begin,
     if (s3_end) *s3_end = e;
     if (rank_begin) *rank_begin = binom4((uint64_t)b);
     if (rank_end) *rank_end = binom4((uint64_t)e);
+    return QS_OK;
+}
+
+int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
+    if (n_taxa < 4 || n_taxa > 32768 || !stats || s3_begin < 0 || s3_end > n_taxa || s3_begin > s3_end) return QS_E_ARG;
+    const int dB = std::max(3, s3_begin), dE = s3_end;
+    const size_t row_bytes = (size_t)((n_taxa + 7) / 8 * 8) * 2;
+    const int max_rows = (int)std::max<size_t>(4, std::min<size_t>((size_t)n_taxa, (24 * 1024) / row_bytes));
+    HostEnum H;
+    build_enum_tables(n_taxa, dB, dE, H);
+    std::vector<RowTask> xt, yt;
+    build_row_tasks(H, n_taxa, dB, dE, max_rows, xt, yt);
+    int64_t items[3] = {0, 0, 0}, slots[3] = {0, 0, 0}, rows = 0, mx = 0, violations = 0, quartets = 0;
+    const int cap[3] = {CR_THREADS, 2 * CR_THREADS, 2 * CR_THREADS};
+    int64_t next_e[3] = {0, 0, 0};
+    auto in_ranges = [](const RowTask& t, int row) {
+        for (int k = 0; k < 3; ++k) if (row >= t.rstart[k] && row < t.rstart[k] + t.rcount[k]) return true;
+        return false;
+    };
+    for (auto* v : {&xt, &yt})
+        for (auto& t : *v) {
+            if (t.e0 != next_e[t.kind] || t.ne < 1 || t.ne > cap[t.kind]) ++violations;       // tasks tile the enumeration
+            next_e[t.kind] = t.e0 + t.ne;
+            items[t.kind] += t.ne; slots[t.kind] += cap[t.kind];
+            const int r = t.rcount[0] + t.rcount[1] + t.rcount[2];
+            rows += r; mx = std::max<int64_t>(mx, r);
+            if (r > max_rows && t.ne > 1) ++violations;
+            for (int i = 0; i < t.ne; ++i) {                                                   // every item's rows are staged, ids are sane
+                int p, q, j, k2;
+                if (t.kind == ITEM_Y) {
+                    cr_decode_y(H.view(), t.e0 + i, n_taxa, dB, p, q, j, k2);
+                    if (!(p >= 1 && p < q && q <= dE - 2 && j < (p + 7) / 8 && k2 * 8 < dE && k2 * 8 + 7 >= cr_dlo(q, dB))) ++violations;
+                } else {
+                    cr_decode_x(t.kind == ITEM_XO ? H.PXO.data() : H.PXD.data(), t.kind, H.xo_diag, t.e0 + i, n_taxa, dB, p, q, j);
+                    if (!(p >= 2 && p < q && q >= dB && q < dE && j < (t.kind == ITEM_XO ? cr_nxo(p, H.xo_diag) : cr_nxd(p, H.xo_diag)))) ++violations;
+                }
+                if (!in_ranges(t, p) || !in_ranges(t, q)) ++violations;
+            }
+        }
+    if (next_e[ITEM_XO] != H.PXO[n_taxa] || next_e[ITEM_XD] != H.PXD[n_taxa] || next_e[ITEM_Y] != H.PY[n_taxa]) ++violations;
+    quartets = (int64_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB));
+    stats[0] = (int64_t)xt.size(); stats[1] = (int64_t)yt.size();
+    stats[2] = items[0]; stats[3] = items[1]; stats[4] = items[2];
+    stats[5] = slots[0]; stats[6] = slots[1]; stats[7] = slots[2];
+    stats[8] = rows; stats[9] = mx; stats[10] = violations; stats[11] = quartets;
     return QS_OK;
 }
 

@@ -136,30 +136,15 @@ def test_bad_tree_encoding_rejected(golden):
     ctx.close()
 
 
-# ---- tiled kernel (large-n path) and table-free mode, forced on small inputs -----------------------
-
-@pytest.fixture
-def force_tiled(monkeypatch):
-    monkeypatch.setenv("QS_FORCE_TILED", "1")
-
-
-@pytest.mark.parametrize("name", golden_cases())
-def test_tiled_kernel_golden(name, golden, force_tiled):
-    g = golden(name)
-    ref_root, ref, flat = load_input(g)
-    with run_ctx(ref, flat) as ctx:
-        assert np.array_equal(ctx.get_counts().astype(np.uint32), g["counts"].astype(np.uint32))
-        lq, qp, eqp = ctx.score(1)
-        bif = bool(np.isfinite(g["qpic"]).any())
-        assert write_annotated_newick(ref_root, ref, lq, qp if bif else None, eqp if bif else None) == g["out_newick"]
-
+# ---- more shapes for the counting kernel, and table-free mode ---------------------------------------------
 
 @pytest.mark.parametrize("n,m,seed,kw", [
-    (40, 300, 31, dict(k_max=10, p_missing=0.1, p_contract=0.1)),
-    (70, 120, 32, dict(k_max=15)),
-    (19, 2300, 33, dict(k_max=4, p_missing=0.2)),          # > 2048 trees: in-kernel fp16 flush
+    (70, 120, 32, dict(k_max=15)),                          # several variable rows per task, class A only
+    (19, 4300, 33, dict(k_max=4, p_missing=0.2)),          # > 4096 trees: more than one fp16 counter chunk, class B
+    (21, 4500, 34, dict(k_max=4)),                          # > 4096 class-A trees
+    (130, 40, 35, dict(k_max=25, p_missing=0.05, p_contract=0.05)),   # wider rows, tasks that split a row's items
 ])
-def test_tiled_kernel_vs_oracle(n, m, seed, kw, force_tiled):
+def test_counts_vs_oracle_more_shapes(n, m, seed, kw):
     s = SyntheticInput(n, m, seed, want_newick=False, **kw)
     ref = flatten_reference(parse_newick(s.ref_newick))
     want = O.count_clades_compact(n, s.flat) // 2
@@ -167,10 +152,15 @@ def test_tiled_kernel_vs_oracle(n, m, seed, kw, force_tiled):
         assert np.array_equal(ctx.get_counts().astype(np.uint32), want)
 
 
+@pytest.fixture
+def tiny_slabs(monkeypatch):
+    monkeypatch.setenv("QS_SLAB_BYTES", "20000")          # table-free mode: force many slabs of the d-range
+
+
 @pytest.mark.parametrize("name", golden_cases())
 @pytest.mark.parametrize("scale,suffix", [(1, ""), (2, "_s")])
-def test_table_free_mode_golden(name, golden, scale, suffix):
-    """-s analogue: no table, quartets are scored inside the counting kernel's epilogue."""
+def test_table_free_mode_golden(name, golden, scale, suffix, tiny_slabs):
+    """-s analogue: no resident table; the d-range is counted and scored slab by slab."""
     from quartetscores_b200 import QS_MODE_TABLE_FREE
     g = golden(name)
     ref_root, ref, flat = load_input(g)
@@ -218,10 +208,7 @@ def _run_shards(ref, flat, G, scale=1, mode=None):
 
 
 @pytest.mark.parametrize("G", [2, 3, 8])
-@pytest.mark.parametrize("tiled", [False, True])
-def test_shards_reproduce_single_shard(G, tiled, monkeypatch):
-    if tiled:
-        monkeypatch.setenv("QS_FORCE_TILED", "1")
+def test_shards_reproduce_single_shard(G):
     s = SyntheticInput(30, 300, 41, k_max=10, p_missing=0.05, p_contract=0.05, want_newick=False)
     ref = flatten_reference(parse_newick(s.ref_newick))
     with run_ctx(ref, s.flat) as ctx:
@@ -235,7 +222,7 @@ def test_shards_reproduce_single_shard(G, tiled, monkeypatch):
 
 
 @pytest.mark.parametrize("G", [2, 4])
-def test_table_free_shards_reproduce_single_shard(G):
+def test_table_free_shards_reproduce_single_shard(G, tiny_slabs):
     from quartetscores_b200 import QS_MODE_TABLE_FREE
     s = SyntheticInput(28, 200, 42, k_max=8, want_newick=False)
     ref = flatten_reference(parse_newick(s.ref_newick))
