@@ -83,7 +83,8 @@ struct CountRowsArgs {
 
 constexpr int CR_THREADS = 512;
 constexpr int CR_MAX_STAGES = 8;
-constexpr int CR_MAX_TPS = 4;
+constexpr int CR_MAX_TPS = 8;
+constexpr int CR_SMEM_HEADER = 128 + 4 * 4096;     // barriers + done counters + the chunk's tree ids (QS_MAX_CHUNK_TREES)
 
 // ---- the enumerations (shared by the host task builder and the kernel) ---------------------------------------
 __host__ __device__ __forceinline__ int cr_nxd(int c, int xo_diag) { return (!xo_diag && c >= 2) ? ((c - 2) >> 3) + 1 : 0; }   // blocks with two taxa below c
@@ -137,29 +138,34 @@ __device__ __forceinline__ void table_red(void* table, int cint_bytes, uint64_t 
 struct RowPipe {
     uint64_t* full;             // [CR_MAX_STAGES] tx barriers
     int* done;                  // [CR_MAX_STAGES] warps finished with the stage
+    int32_t* trees;             // [QS_MAX_CHUNK_TREES] tree ids of the current chunk (order[t0..t1)), staged once per task
     unsigned char* bufs;
     uint32_t stage_bytes;
     uint32_t phase;             // bit s = parity to wait for on full[s]
 };
 
-// Stream the trees [t0,t1) of the class-sorted order through the pipeline, trees_per_stage at a time; f(base)
-// is called once per tree with the shared-memory address of its staged rows.  Warps run independently: the
-// last warp to finish a stage refills it (no CTA-wide barrier inside the loop).
-template <class F>
-__device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, const RowTask& T, int t0, int t1, F&& f) {
+// Stream the trees [t0,t1) of the class-sorted order through the pipeline, trees_per_stage at a time.  Per tree,
+// ld(base) fetches the thread's operands from the staged rows at `base` and mt(operands) does the compares; with
+// PF the operands of the next tree of the stage are fetched before the math of the current one (the LDS latency
+// otherwise shows up as a short-scoreboard stall at the top of every tree: profiles/r01_e_*).  Warps run
+// independently: the last warp to finish a stage refills it (no CTA-wide barrier inside the loop).  The chunk's tree
+// ids are copied to shared memory once per task, so no warp waits on global memory inside the loop.
+template <bool PF, class LD, class MT>
+__device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, const RowTask& T, int t0, int t1, LD&& ld, MT&& mt) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int tps = a.trees_per_stage;
-    const int nst = (t1 - t0 + tps - 1) / tps;
+    const int ntrees = t1 - t0;
+    const int nst = (ntrees + tps - 1) / tps;
     const size_t tree_elems = (size_t)a.n * a.n_pad;
     const uint32_t task_slot = (uint32_t)(T.rcount[0] + T.rcount[1] + T.rcount[2]) * a.row_bytes;       // bytes actually staged per tree
-    // lanes 0..tps-1 of the calling warp copy the rows of the trees of stage st (ids in `tree`, -1 = none)
-    auto issue = [&](int st, int buf, int tree) {
-        const int nt = min(tps, (t1 - t0) - st * tps);
+    // lanes 0..tps-1 of the calling warp copy the rows of the trees of stage st
+    auto issue = [&](int st, int buf) {
+        const int nt = min(tps, ntrees - st * tps);
         if (lane == 0) mbar_expect_tx(&P.full[buf], (uint32_t)nt * task_slot);
         __syncwarp();
         if (lane < nt) {
             unsigned char* dst = P.bufs + (size_t)buf * P.stage_bytes + (size_t)lane * a.slot_bytes;
-            const __half* src = a.D + (size_t)tree * tree_elems;
+            const __half* src = a.D + (size_t)P.trees[st * tps + lane] * tree_elems;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 if (T.rcount[k] > 0) bulk_g2s(dst, src + (size_t)T.rstart[k] * a.n_pad, (uint32_t)T.rcount[k] * a.row_bytes, &P.full[buf]);
@@ -167,33 +173,38 @@ __device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, 
             }
         }
     };
-    auto tree_of = [&](int st) -> int {      // tree id this lane would copy for stage st
-        const int t = t0 + st * tps + lane;
-        return (lane < tps && st < nst && t < t1) ? a.order[t] : -1;
-    };
-    __syncthreads();                 // the previous task's readers are done with every stage
+    __syncthreads();                 // the previous task's readers are done with every stage and with P.trees
+    for (int i = tid; i < ntrees; i += CR_THREADS) P.trees[i] = a.order[t0 + i];
     if (tid < a.n_stages) P.done[tid] = 0;
-    if (tid < 32)
-        for (int s = 0; s < a.n_stages && s < nst; ++s) issue(s, s, tree_of(s));
     __syncthreads();
+    if (tid < 32)
+        for (int s = 0; s < a.n_stages && s < nst; ++s) issue(s, s);
     int buf = 0;
     for (int st = 0; st < nst; ++st) {
-        // every warp prefetches the tree ids of the stage that will refill this buffer, so that whichever warp
-        // leaves it last can issue the copies without waiting on global memory
-        const int nxt = tree_of(st + a.n_stages);
         mbar_wait(&P.full[buf], (P.phase >> buf) & 1u);
         P.phase ^= (1u << buf);
-        const int nt = min(tps, (t1 - t0) - st * tps);
+        const int nt = min(tps, ntrees - st * tps);
         const unsigned char* base = P.bufs + (size_t)buf * P.stage_bytes;
+        if (PF) {
+            auto cur = ld(base);
 #pragma unroll 1
-        for (int tt = 0; tt < nt; ++tt, base += a.slot_bytes) f(base);
+            for (int tt = 0; tt < nt; ++tt) {
+                if (tt + 1 < nt) base += a.slot_bytes;       // (the last tree of a stage re-reads itself: no branch around the loads)
+                auto nx = ld(base);
+                mt(cur);
+                cur = nx;
+            }
+        } else {
+#pragma unroll 1
+            for (int tt = 0; tt < nt; ++tt, base += a.slot_bytes) mt(ld(base));
+        }
         __syncwarp();
         int last = 0;
         if (lane == 0) last = (atomicAdd(&P.done[buf], 1) == CR_THREADS / 32 - 1);
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {                                  // last warp out refills the stage
             if (lane == 0) P.done[buf] = 0;
-            if (st + a.n_stages < nst) issue(st + a.n_stages, buf, nxt);
+            if (st + a.n_stages < nst) issue(st + a.n_stages, buf);
         }
         buf = (buf + 1 == a.n_stages) ? 0 : buf + 1;
     }
@@ -216,7 +227,8 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
     RowPipe P;
     P.full = reinterpret_cast<uint64_t*>(smem);
     P.done = reinterpret_cast<int*>(smem + 64);
-    P.bufs = smem + 128;
+    P.trees = reinterpret_cast<int32_t*>(smem + 128);
+    P.bufs = smem + CR_SMEM_HEADER;
     P.stage_bytes = (uint32_t)a.trees_per_stage * a.slot_bytes;
     P.phase = 0;
     const int tid = threadIdx.x;
@@ -264,9 +276,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
             const uint32_t rp = valid ? cr_row_off(T, c, rb) : 0u, rq = valid ? cr_row_off(T, d, rb) : 0u;
             const uint32_t oPu = rp + ia * 16u, oQu = rq + ia * 16u, oPv = rp + ib * 16u, oQv = rq + ib * 16u;
             XCounters x; zero(x);
-            stream_rows(a, P, T, t0, t1, [&](const unsigned char* s) {
-                step_gt_lt(x, BlockRows{lds128(s, oPu), lds128(s, oQu), lds128(s, oPv), lds128(s, oQv)});
-            });
+            stream_rows<true>(a, P, T, t0, t1,
+                [&](const unsigned char* s) { return BlockRows{lds128(s, oPu), lds128(s, oQu), lds128(s, oPv), lds128(s, oQv)}; },
+                [&](const BlockRows& r) { step_gt_lt(x, r); });
             if (valid) {
                 const uint64_t rcd = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
 #pragma unroll
@@ -296,10 +308,9 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
             const uint32_t oAp = (vA ? cr_row_off(T, cA, rb) : 0u) + jA * 16u, oAq = (vA ? cr_row_off(T, dA, rb) : 0u) + jA * 16u;
             const uint32_t oBp = (vB ? cr_row_off(T, cB, rb) : 0u) + jB * 16u, oBq = (vB ? cr_row_off(T, dB, rb) : 0u) + jB * 16u;
             GCounters ga, gb; zero(ga); zero(gb);
-            stream_rows(a, P, T, t0, t1, [&](const unsigned char* s) {
-                step_gt_diag(ga, lds128(s, oAp), lds128(s, oAq));
-                step_gt_diag(gb, lds128(s, oBp), lds128(s, oBq));
-            });
+            stream_rows<true>(a, P, T, t0, t1,
+                [&](const unsigned char* s) { return BlockRows{lds128(s, oAp), lds128(s, oAq), lds128(s, oBp), lds128(s, oBq)}; },
+                [&](const BlockRows& r) { step_gt_diag(ga, r.pu, r.qu); step_gt_diag(gb, r.pv, r.qv); });
             auto flush = [&](int c, int d, int blk, const GCounters& g) {
                 const int x0 = blk * 8;
                 const uint64_t rcd = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
@@ -334,10 +345,13 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
             const uint32_t oApu = pA + iaA * 16u, oAqu = qA + iaA * 16u, oApv = pA + idA * 16u, oAqv = qA + idA * 16u;
             const uint32_t oBpu = pB + iaB * 16u, oBqu = qB + iaB * 16u, oBpv = pB + idB * 16u, oBqv = qB + idB * 16u;
             GCounters ga, gb; zero(ga); zero(gb);
-            stream_rows(a, P, T, t0, t1, [&](const unsigned char* s) {
-                step_gt(ga, BlockRows{lds128(s, oApu), lds128(s, oAqu), lds128(s, oApv), lds128(s, oAqv)});
-                step_gt(gb, BlockRows{lds128(s, oBpu), lds128(s, oBqu), lds128(s, oBpv), lds128(s, oBqv)});
-            });
+            struct TwoBlocks { BlockRows a, b; };
+            stream_rows<false>(a, P, T, t0, t1,
+                [&](const unsigned char* s) {
+                    return TwoBlocks{BlockRows{lds128(s, oApu), lds128(s, oAqu), lds128(s, oApv), lds128(s, oAqv)},
+                                     BlockRows{lds128(s, oBpu), lds128(s, oBqu), lds128(s, oBpv), lds128(s, oBqv)}};
+                },
+                [&](const TwoBlocks& r) { step_gt(ga, r.a); step_gt(gb, r.b); });
             auto flush = [&](int b, int c, int ia, int id, const GCounters& g) {
                 const int dlo = max(c + 1, a.d_begin);
 #pragma unroll

@@ -122,6 +122,113 @@ __global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
     if ((threadIdx.x & 31) == 0 && local_max > 0) atomicMax(a.max_dist, local_max);
 }
 
+// ---- warp-per-tree variant for small gene trees ------------------------------------------------------------
+// The CTA-per-tree kernel above leaves 255 threads idle while one thread walks the tree, and at 100 taxa that
+// serial walk is most of its time (0.78 ms for 10,000 trees, profiles/r01_e_launches.csv).  Here every WARP owns a
+// tree: up to 64 trees per SM are in flight, lane 0 runs three short index-order passes instead of a stack DFS
+// (valid because parent[i] < i): depths + child counts (forward), leaves per subtree (backward), first leaf
+// position of every subtree (forward).  Everything else — validation, the leaf arrays, the turning depths
+// lh[q] = depth of lca(leaf q, leaf q+1), written by the unique non-first child whose subtree starts at q+1 — and
+// the pair sweep run on all 32 lanes.  Any planar order gives the same matrix; this one lists children by index.
+constexpr int DW_WARPS = 8;
+constexpr int DW_ARRAYS = 10;    // int16 arrays of max_nodes entries per warp
+__host__ __device__ __forceinline__ size_t dist_warp_smem_per_warp(int max_nodes, int n) {
+    return (size_t)DW_ARRAYS * 2 * ((max_nodes + 7) / 8 * 8) + (size_t)((n + 31) / 32) * 4;
+}
+
+__global__ void __launch_bounds__(32 * DW_WARPS) qs_dist_warp_kernel(DistArgs a) {
+    extern __shared__ __align__(16) unsigned char sm_w[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NP = (a.max_nodes + 7) / 8 * 8, nw = (a.n + 31) / 32;
+    unsigned char* mine = sm_w + (size_t)warp * dist_warp_smem_per_warp(a.max_nodes, a.n);
+    int16_t* par = reinterpret_cast<int16_t*>(mine);   // parent
+    int16_t* dep = par + NP;                           // depth
+    int16_t* cnt = dep + NP;                           // number of children
+    int16_t* lfc = cnt + NP;                           // leaves in the subtree
+    int16_t* off = lfc + NP;                           // tour position of the subtree's first leaf
+    int16_t* nf = off + NP;                            // next free position while children are placed
+    int16_t* lid = nf + NP;                            // taxon id (-1: none)
+    int16_t* ltid = lid + NP;                          // per tour position: taxon id,
+    int16_t* ldep = ltid + NP;                         //   depth,
+    int16_t* lh = ldep + NP;                           //   depth of lca(leaf q, leaf q+1)
+    uint32_t* seen = reinterpret_cast<uint32_t*>(lh + NP);
+    const unsigned FULL = 0xffffffffu;
+    int local_max = 0;
+    const int gw = blockIdx.x * DW_WARPS + warp, stride = gridDim.x * DW_WARPS;
+
+    for (int t = gw; t < a.m; t += stride) {
+        const int64_t o = a.node_off[t];
+        const int N = (int)(a.node_off[t + 1] - o);
+        int bad = 0;
+        __syncwarp();
+        for (int i = lane; i < N; i += 32) {
+            int p = a.parent[o + i];
+            if (i > 0 && (p < 0 || p >= i)) { bad = 1; p = 0; }
+            par[i] = (int16_t)p; cnt[i] = 0; lfc[i] = 0;
+            const int id = a.leaf_id[o + i];
+            lid[i] = (int16_t)((id >= 0 && id < a.n) ? id : (id < 0 ? -1 : -2));
+        }
+        for (int i = lane; i < nw; i += 32) seen[i] = 0u;
+        __syncwarp();
+        if (lane == 0) {
+            dep[0] = 0; off[0] = 0; nf[0] = 0;
+            for (int i = 1; i < N; ++i) { const int p = par[i]; dep[i] = dep[p] + 1; cnt[p] = cnt[p] + 1; }
+            for (int i = N - 1; i >= 1; --i) { const int l = cnt[i] == 0 ? 1 : lfc[i]; lfc[i] = (int16_t)l; lfc[par[i]] = lfc[par[i]] + l; }
+            if (cnt[0] == 0) lfc[0] = 1;
+            for (int i = 1; i < N; ++i) { const int p = par[i]; const int q = nf[p]; off[i] = (int16_t)q; nf[i] = (int16_t)q; nf[p] = (int16_t)(q + lfc[i]); }
+        }
+        __syncwarp();
+        // validation, degrees, leaf arrays, turning depths: all lanes
+        int maxdeg = 0;
+        for (int i = lane; i < N; i += 32) {
+            const int c = cnt[i], id = lid[i];
+            maxdeg = max(maxdeg, c + (i > 0 ? 1 : 0));
+            if (c == 0) {
+                if (id < 0) bad = max(bad, 2);
+                else {
+                    const uint32_t bit = 1u << (id & 31);
+                    if (atomicOr(&seen[id >> 5], bit) & bit) bad = max(bad, 3);
+                    ltid[off[i]] = (int16_t)id; ldep[off[i]] = dep[i];
+                }
+            } else if (i > 0 && id != -1) bad = max(bad, 4);            // inner node carrying a taxon id
+            if (i > 0 && off[i] > off[par[i]]) lh[off[i] - 1] = dep[par[i]];
+        }
+        for (int s = 16; s > 0; s >>= 1) { bad = max(bad, __shfl_xor_sync(FULL, bad, s)); maxdeg = max(maxdeg, __shfl_xor_sync(FULL, maxdeg, s)); }
+        __syncwarp();
+        const int k = bad ? 0 : (int)lfc[0];
+        if (lane == 0) {
+            if (bad) atomicCAS(a.max_dist + 1, 0, bad);
+            a.tree_class[t] = (!bad && k == a.n && maxdeg <= 3) ? 0 : 1;
+        }
+        __half* Dt = a.D + (size_t)t * a.n * a.n_pad;
+        for (int i0 = 0; i0 < k; i0 += 32) {
+            const int i = i0 + lane;
+            const bool act = i < k;
+            const int ti = act ? ltid[i] : 0, di = act ? ldep[i] : 0;
+            if (act) Dt[(size_t)ti * a.n_pad + ti] = __int2half_rn(0);
+            int mn = 0x7fff;
+            for (int j = i0 + 1; j < k; ++j) {                   // j ascending, lanes with i < j
+                if (act && j > i) {
+                    mn = min(mn, (int)lh[j - 1]);
+                    const int d = di + ldep[j] - 2 * mn;
+                    local_max = max(local_max, d);
+                    Dt[(size_t)ltid[j] * a.n_pad + ti] = __int2half_rn(d);
+                }
+            }
+            mn = 0x7fff;
+            for (int j = min(k - 1, i0 + 31) - 1; j >= 0; --j) {  // j descending, lanes with i > j
+                if (act && j < i) {
+                    mn = min(mn, (int)lh[j]);
+                    const int d = di + ldep[j] - 2 * mn;
+                    Dt[(size_t)ltid[j] * a.n_pad + ti] = __int2half_rn(d);
+                }
+            }
+        }
+    }
+    for (int s = 16; s > 0; s >>= 1) local_max = max(local_max, __shfl_xor_sync(FULL, local_max, s));
+    if (lane == 0 && local_max > 0) atomicMax(a.max_dist, local_max);
+}
+
 // class-sorted tree order (stable partition: class-A trees first) and |A|; one CTA
 __global__ void __launch_bounds__(1024) qs_order_kernel(const int32_t* __restrict__ tree_class, int m, int32_t* __restrict__ order, int32_t* __restrict__ n_class_a) {
     __shared__ int cntA[1024];

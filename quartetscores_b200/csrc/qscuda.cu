@@ -88,6 +88,7 @@ struct qs_ctx {
     int plan_dB = -1, plan_dE = -1, plan_nx = 0, plan_ny = 0, plan_max_rows = 1;
     int64_t* d_enum = nullptr;   // PXO | PXD | PY | CD prefix tables of the plan
     bool counted = false;
+    bool counted_once = false;   // n_class_a holds the class split of an earlier qs_count on this context
 
     // scoring
     unsigned long long* d_pair_sums = nullptr;
@@ -198,12 +199,21 @@ int run_distances(qs_ctx* c) {
     da.node_off = c->d_off; da.parent = c->d_parent; da.leaf_id = c->d_leaf;
     da.m = (int)c->m; da.n = c->n; da.n_pad = c->n_pad; da.max_nodes = c->max_nodes; da.D = c->d_D; da.max_dist = c->d_flags;
     da.tree_class = c->d_class;
-    size_t smem = (size_t)8 * 4 * c->max_nodes + (size_t)((c->n + 31) / 32) * 4;
-    if (smem > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "gene tree with %d nodes exceeds the distance kernel's shared-memory budget", c->max_nodes);
-    QS_CUDA(c, cudaFuncSetAttribute(qs_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = std::max(1, std::min(8, (int)((size_t)c->smem_optin / std::max<size_t>(smem, 1024))));
-    int grid = (int)std::min<int64_t>(c->m, (int64_t)c->num_sms * per_sm);
-    qs_dist_kernel<<<grid, 256, smem, c->stream>>>(da);
+    const size_t warp_smem = dist_warp_smem_per_warp(c->max_nodes, c->n) * DW_WARPS;
+    if (c->max_nodes <= 2048 && c->n <= 32767 && warp_smem <= (size_t)c->smem_optin) {
+        // small trees: one warp per tree, as many trees in flight as shared memory allows
+        QS_CUDA(c, cudaFuncSetAttribute(qs_dist_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
+        int per_sm = std::max(1, std::min(8, (int)((size_t)c->smem_optin / (warp_smem + 1024))));
+        int grid = (int)std::min<int64_t>((c->m + DW_WARPS - 1) / DW_WARPS, (int64_t)c->num_sms * per_sm);
+        qs_dist_warp_kernel<<<grid, 32 * DW_WARPS, warp_smem, c->stream>>>(da);
+    } else {
+        size_t smem = (size_t)8 * 4 * c->max_nodes + (size_t)((c->n + 31) / 32) * 4;
+        if (smem > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "gene tree with %d nodes exceeds the distance kernel's shared-memory budget", c->max_nodes);
+        QS_CUDA(c, cudaFuncSetAttribute(qs_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = std::max(1, std::min(8, (int)((size_t)c->smem_optin / std::max<size_t>(smem, 1024))));
+        int grid = (int)std::min<int64_t>(c->m, (int64_t)c->num_sms * per_sm);
+        qs_dist_kernel<<<grid, 256, smem, c->stream>>>(da);
+    }
     c->launches++;
     QS_CUDA(c, cudaGetLastError());
     qs_order_kernel<<<1, 1024, 0, c->stream>>>(c->d_class, (int)c->m, c->d_order, c->d_nA);
@@ -307,7 +317,7 @@ int ensure_plan(qs_ctx* c, int dB, int dE) {
     const size_t row_bytes = (size_t)c->n_pad * 2;
     // shared-memory budget per staged tree: ~24 KB (the whole matrix when n <= ~110), at least 4 rows
     const int max_rows = (int)std::max<size_t>(4, std::min<size_t>((size_t)c->n, (24 * 1024) / row_bytes));
-    if ((size_t)max_rows * row_bytes * 2 + 256 > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: matrix rows of %zu bytes are too long for the counting kernel's shared-memory pipeline", c->n, row_bytes);
+    if ((size_t)max_rows * row_bytes * 2 + CR_SMEM_HEADER + 256 > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: matrix rows of %zu bytes are too long for the counting kernel's shared-memory pipeline", c->n, row_bytes);
     HostEnum H;
     build_enum_tables(c->n, dB, dE, H);
     std::vector<RowTask> xt, yt;
@@ -373,21 +383,29 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table) {
     a.n = c->n; a.n_pad = c->n_pad; a.m = (int)c->m; a.d_begin = dB; a.d_end = dE;
     a.row_bytes = (uint32_t)c->n_pad * 2u;
     a.slot_bytes = (uint32_t)c->plan_max_rows * a.row_bytes;
-    // pipeline: trees_per_stage x n_stages slots of slot_bytes
-    const size_t budget = (size_t)c->smem_optin - 256;
+    // pipeline: trees_per_stage x n_stages slots of slot_bytes (8 trees per stage halve the per-stage hand-over cost)
+    const size_t budget = (size_t)c->smem_optin - CR_SMEM_HEADER - 256;
     int tps = CR_MAX_TPS;
-    while (tps > 1 && (size_t)2 * tps * a.slot_bytes > budget) --tps;
+    while (tps > 1 && (size_t)3 * tps * a.slot_bytes > budget) --tps;
     int nst = (int)std::min<size_t>(CR_MAX_STAGES, budget / ((size_t)tps * a.slot_bytes));
     if (nst < 2) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: two pipeline stages of %u-byte row slots do not fit in shared memory", c->n, a.slot_bytes);
     a.trees_per_stage = tps; a.n_stages = nst;
-    // tree chunks: <= 4096 trees (fp16 counters), and enough tasks for the dynamic scheduler to balance (~8 per SM)
-    const int64_t base = std::max<int64_t>(1, (int64_t)a.n_x + a.n_y);
-    int64_t want_chunks = std::max<int64_t>(1, (8LL * c->num_sms + base - 1) / base);
-    int64_t chunk = std::max<int64_t>(256, (c->m + want_chunks - 1) / want_chunks);
-    a.chunk_trees = (int)std::min<int64_t>(QS_MAX_CHUNK_TREES, chunk);
-    const size_t smem = 128 + (size_t)nst * tps * a.slot_bytes;
+    // tree chunks: <= 4096 trees (fp16 counters) and >= 256; among the chunk counts that give the dynamic scheduler
+    // 6..16 tasks per SM pick the one whose last round of tasks is fullest (tasks of one kind take the same time)
+    const bool all_a = !c->counted_once || c->n_class_a == c->m;
+    const int64_t base = std::max<int64_t>(1, (int64_t)a.n_x + (all_a ? 0 : a.n_y));
+    int64_t best_k = 1; double best_eff = -1;
+    for (int64_t k = std::max<int64_t>(1, (c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES); k <= std::max<int64_t>(1, c->m / 256); ++k) {
+        const int64_t T = base * k, rounds = (T + c->num_sms - 1) / c->num_sms;
+        if (rounds > 16 && best_eff >= 0) break;
+        double eff = (double)T / (double)(rounds * c->num_sms);
+        if (rounds < 6) eff *= 0.5 + rounds / 12.0;                 // too few tasks per SM: uneven task lengths dominate
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_k = k; }
+    }
+    a.chunk_trees = (int)std::min<int64_t>(QS_MAX_CHUNK_TREES, std::max<int64_t>(1, (c->m + best_k - 1) / best_k));
+    const size_t smem = CR_SMEM_HEADER + (size_t)nst * tps * a.slot_bytes;
     QS_CUDA(c, cudaFuncSetAttribute(qs_count_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t max_tasks = base * 2 * ((c->m + a.chunk_trees - 1) / a.chunk_trees + 1);
+    const int64_t max_tasks = ((int64_t)a.n_x + a.n_y) * 2 * ((c->m + a.chunk_trees - 1) / a.chunk_trees + 1);
     if (max_tasks > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
     const int grid = (int)std::min<int64_t>(max_tasks, c->num_sms);
     qs_count_rows_kernel<<<grid, CR_THREADS, smem, c->stream>>>(a);
@@ -864,7 +882,7 @@ int qs_count(qs_ctx* ctx) {
     QS_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
     QS_CUDA(ctx, cudaMemcpyAsync(&nA, ctx->d_nA, sizeof(nA), cudaMemcpyDeviceToHost, ctx->stream));
     QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->n_class_a = nA;
+    ctx->n_class_a = nA; ctx->counted_once = true;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->dist_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->count_ms = ms;
