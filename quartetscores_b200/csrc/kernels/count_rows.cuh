@@ -76,9 +76,8 @@ struct CountRowsArgs {
     uint64_t rank_base;
     int n, n_pad, m;
     int d_begin, d_end;         // shard: quartets with d in [d_begin, d_end)
-    int n_stages, trees_per_stage;
     uint32_t row_bytes;         // n_pad * 2
-    uint32_t slot_bytes;        // shared-memory bytes reserved per tree = (max rows of a task) * row_bytes
+    uint32_t ring_bytes;        // shared memory available to the staging ring (every task sizes its own stages from it)
 };
 
 constexpr int CR_THREADS = 512;
@@ -140,7 +139,6 @@ struct RowPipe {
     int* done;                  // [CR_MAX_STAGES] warps finished with the stage
     int32_t* trees;             // [QS_MAX_CHUNK_TREES] tree ids of the current chunk (order[t0..t1)), staged once per task
     unsigned char* bufs;
-    uint32_t stage_bytes;
     uint32_t phase;             // bit s = parity to wait for on full[s]
 };
 
@@ -153,18 +151,25 @@ struct RowPipe {
 template <bool PF, class LD, class MT>
 __device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, const RowTask& T, int t0, int t1, LD&& ld, MT&& mt) {
     const int tid = threadIdx.x, lane = tid & 31;
-    const int tps = a.trees_per_stage;
     const int ntrees = t1 - t0;
-    const int nst = (ntrees + tps - 1) / tps;
     const size_t tree_elems = (size_t)a.n * a.n_pad;
-    const uint32_t task_slot = (uint32_t)(T.rcount[0] + T.rcount[1] + T.rcount[2]) * a.row_bytes;       // bytes actually staged per tree
+    // pipeline geometry of THIS task: a staged tree takes only the rows the task touches (a few KB for most tasks, the
+    // whole matrix only for the few tasks with tiny c), so the ring is as deep as the shared-memory budget allows:
+    // up to CR_MAX_TPS trees per stage x CR_MAX_STAGES stages.  A shallow ring (sized for the worst task) left the
+    // warps waiting on the refill latency for 14 % of their time (profiles/r01_f_*).
+    const uint32_t slot = (uint32_t)(T.rcount[0] + T.rcount[1] + T.rcount[2]) * a.row_bytes;            // bytes staged per tree
+    int tps = CR_MAX_TPS;
+    while (tps > 1 && (uint32_t)(3 * tps) * slot > a.ring_bytes) --tps;
+    const int n_stages = min(CR_MAX_STAGES, (int)(a.ring_bytes / ((uint32_t)tps * slot)));
+    const uint32_t stage_bytes = (uint32_t)tps * slot;
+    const int nst = (ntrees + tps - 1) / tps;
     // lanes 0..tps-1 of the calling warp copy the rows of the trees of stage st
     auto issue = [&](int st, int buf) {
         const int nt = min(tps, ntrees - st * tps);
-        if (lane == 0) mbar_expect_tx(&P.full[buf], (uint32_t)nt * task_slot);
+        if (lane == 0) mbar_expect_tx(&P.full[buf], (uint32_t)nt * slot);
         __syncwarp();
         if (lane < nt) {
-            unsigned char* dst = P.bufs + (size_t)buf * P.stage_bytes + (size_t)lane * a.slot_bytes;
+            unsigned char* dst = P.bufs + (size_t)buf * stage_bytes + (size_t)lane * slot;
             const __half* src = a.D + (size_t)P.trees[st * tps + lane] * tree_elems;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
@@ -175,28 +180,28 @@ __device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, 
     };
     __syncthreads();                 // the previous task's readers are done with every stage and with P.trees
     for (int i = tid; i < ntrees; i += CR_THREADS) P.trees[i] = a.order[t0 + i];
-    if (tid < a.n_stages) P.done[tid] = 0;
+    if (tid < CR_MAX_STAGES) P.done[tid] = 0;
     __syncthreads();
     if (tid < 32)
-        for (int s = 0; s < a.n_stages && s < nst; ++s) issue(s, s);
+        for (int s = 0; s < n_stages && s < nst; ++s) issue(s, s);
     int buf = 0;
     for (int st = 0; st < nst; ++st) {
         mbar_wait(&P.full[buf], (P.phase >> buf) & 1u);
         P.phase ^= (1u << buf);
         const int nt = min(tps, ntrees - st * tps);
-        const unsigned char* base = P.bufs + (size_t)buf * P.stage_bytes;
+        const unsigned char* base = P.bufs + (size_t)buf * stage_bytes;
         if (PF) {
             auto cur = ld(base);
 #pragma unroll 1
             for (int tt = 0; tt < nt; ++tt) {
-                if (tt + 1 < nt) base += a.slot_bytes;       // (the last tree of a stage re-reads itself: no branch around the loads)
+                if (tt + 1 < nt) base += slot;               // (the last tree of a stage re-reads itself: no branch around the loads)
                 auto nx = ld(base);
                 mt(cur);
                 cur = nx;
             }
         } else {
 #pragma unroll 1
-            for (int tt = 0; tt < nt; ++tt, base += a.slot_bytes) mt(ld(base));
+            for (int tt = 0; tt < nt; ++tt, base += slot) mt(ld(base));
         }
         __syncwarp();
         int last = 0;
@@ -204,9 +209,9 @@ __device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, 
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {                                  // last warp out refills the stage
             if (lane == 0) P.done[buf] = 0;
-            if (st + a.n_stages < nst) issue(st + a.n_stages, buf);
+            if (st + n_stages < nst) issue(st + n_stages, buf);
         }
-        buf = (buf + 1 == a.n_stages) ? 0 : buf + 1;
+        buf = (buf + 1 == n_stages) ? 0 : buf + 1;
     }
 }
 
@@ -229,7 +234,6 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
     P.done = reinterpret_cast<int*>(smem + 64);
     P.trees = reinterpret_cast<int32_t*>(smem + 128);
     P.bufs = smem + CR_SMEM_HEADER;
-    P.stage_bytes = (uint32_t)a.trees_per_stage * a.slot_bytes;
     P.phase = 0;
     const int tid = threadIdx.x;
     if (tid == 0) {

@@ -382,14 +382,12 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table) {
     a.task_counter = c->d_counter; a.table = table; a.cint_bytes = c->cint_bytes; a.rank_base = rb;
     a.n = c->n; a.n_pad = c->n_pad; a.m = (int)c->m; a.d_begin = dB; a.d_end = dE;
     a.row_bytes = (uint32_t)c->n_pad * 2u;
-    a.slot_bytes = (uint32_t)c->plan_max_rows * a.row_bytes;
-    // pipeline: trees_per_stage x n_stages slots of slot_bytes (8 trees per stage halve the per-stage hand-over cost)
-    const size_t budget = (size_t)c->smem_optin - CR_SMEM_HEADER - 256;
-    int tps = CR_MAX_TPS;
-    while (tps > 1 && (size_t)3 * tps * a.slot_bytes > budget) --tps;
-    int nst = (int)std::min<size_t>(CR_MAX_STAGES, budget / ((size_t)tps * a.slot_bytes));
-    if (nst < 2) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: two pipeline stages of %u-byte row slots do not fit in shared memory", c->n, a.slot_bytes);
-    a.trees_per_stage = tps; a.n_stages = nst;
+    // staging ring: all the shared memory the CTA can get; every task sizes its own stages from the rows it touches
+    // (kernels/count_rows.cuh: stream_rows), the largest task must fit twice
+    const size_t budget = ((size_t)c->smem_optin - CR_SMEM_HEADER - 256) & ~(size_t)127;
+    const size_t max_slot = (size_t)c->plan_max_rows * a.row_bytes;
+    if (2 * max_slot > budget) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: two pipeline stages of %zu-byte row slots do not fit in shared memory", c->n, max_slot);
+    a.ring_bytes = (uint32_t)budget;
     // tree chunks: <= 4096 trees (fp16 counters) and >= 256; among the chunk counts that give the dynamic scheduler
     // 6..16 tasks per SM pick the one whose last round of tasks is fullest (tasks of one kind take the same time)
     const bool all_a = !c->counted_once || c->n_class_a == c->m;
@@ -403,7 +401,7 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table) {
         if (eff > best_eff + 1e-9) { best_eff = eff; best_k = k; }
     }
     a.chunk_trees = (int)std::min<int64_t>(QS_MAX_CHUNK_TREES, std::max<int64_t>(1, (c->m + best_k - 1) / best_k));
-    const size_t smem = CR_SMEM_HEADER + (size_t)nst * tps * a.slot_bytes;
+    const size_t smem = CR_SMEM_HEADER + budget;
     QS_CUDA(c, cudaFuncSetAttribute(qs_count_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t max_tasks = ((int64_t)a.n_x + a.n_y) * 2 * ((c->m + a.chunk_trees - 1) / a.chunk_trees + 1);
     if (max_tasks > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
