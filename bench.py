@@ -40,7 +40,13 @@ WORKLOADS = {
     "cfg2": dict(n_taxa=100, n_trees=10000, seed=2000, k_max=20, label="100 taxa x 10,000 gene trees, full uint16 lookup table (3.9M quartets) on 1 B200"),
     "cfg3": dict(n_taxa=500, n_trees=5000, seed=3000, k_max=20, p_missing=0.1, p_contract=0.05,
                  label="500 taxa x 5,000 gene trees with missing taxa and multifurcations, uint16 table (15.4 GB)"),
+    # configs[3..4]: the 248.5 GB / 3.99 TB tables do not fit one GPU -> table-free (slab-streamed) mode unless the shard's table fits
+    "cfg4": dict(n_taxa=1000, n_trees=2000, seed=4000, k_max=20,
+                 label="1,000 taxa x 2,000 gene trees, 248.5 GB uint16 table: sharded in HBM when a shard fits, else table-free slabs"),
+    "cfg5": dict(n_taxa=2000, n_trees=1000, seed=5000, k_max=20,
+                 label="-s savemem mode, 2,000 taxa x 1,000 gene trees, table-free: counts evaluated on the fly, never stored"),
 }
+TABLE_BYTES_LIMIT = 120e9      # a shard's uint16 table above this is not kept resident (180 GB HBM3e minus matrices and slack)
 # one packed fp16x2 compare (HSET2 lane-op) decides one topology slot of TWO quartets.  A gene tree that
 # resolves every quartet (class A) needs 2 slots per quartet x tree = 1.0 HSET2 lane-op per evaluation, any other
 # tree (class B) needs 3 = 1.5.
@@ -165,9 +171,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (long workloads: cfg4/cfg5 exploration runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "ours" and not args.no_e2e:
+        args.warmup = max(args.warmup, 3)       # timing rule: W >= 3 (exploration runs with --no-e2e may use fewer)
 
     wname = args.workload or "cfg2"
     w = WORKLOADS[wname]
@@ -182,8 +190,9 @@ def main():
     import numpy as np
     import torch
 
-    from quartetscores_b200 import Context
+    from quartetscores_b200 import QS_MODE_TABLE, QS_MODE_TABLE_FREE, Context
     from quartetscores_b200.computer import cint_bytes_for
+    from quartetscores_b200.multi import shard_bounds
     from quartetscores_b200.multi import score_distributed
     from quartetscores_b200.newick import flatten_reference, parse_newick
 
@@ -197,6 +206,9 @@ def main():
     if world > 1:
         import torch.distributed as dist
 
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     n, m = w["n_taxa"], w["n_trees"]
@@ -209,7 +221,12 @@ def main():
     h_par = torch.from_numpy(np.ascontiguousarray(flat.parent)).pin_memory()
     h_leaf = torch.from_numpy(np.ascontiguousarray(flat.leaf_lookup_id)).pin_memory()
 
-    ctx = Context(n, cint_bytes_for(m), device=local_rank, shard_index=rank, shard_count=world)
+    _, _, rb0, rb1 = shard_bounds(n, rank, world)
+    table_free = wname == "cfg5" or (rb1 - rb0) * 3 * cint_bytes_for(m) > TABLE_BYTES_LIMIT
+    ctx = Context(n, cint_bytes_for(m), mode=QS_MODE_TABLE_FREE if table_free else QS_MODE_TABLE, device=local_rank, shard_index=rank, shard_count=world)
+    if wname == "cfg5":
+        ctx.set_count_scale(2)          # the reference's -s table semantics (doubled, CINT-wrapped counts)
+    score_scale = 2 if wname == "cfg5" else 1
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     ctx.set_reference(ref)
@@ -220,7 +237,7 @@ def main():
         ctx.add_trees_ptr(flat.n_trees, h_off.data_ptr(), h_par.data_ptr(), h_leaf.data_ptr())
 
     def score():
-        return score_distributed(ctx, 1)     # 1 GPU: qs_score; N GPUs: partial scan + all-reduce(min) + all-reduce(sum) + finalise
+        return score_distributed(ctx, score_scale)     # 1 GPU: qs_score; N GPUs: partial scan + all-reduce(min) + all-reduce(sum) + finalise
 
     def step_resident():
         ctx.count()
@@ -266,10 +283,13 @@ def main():
     ms_res, scores, kt, span = timed(step_resident, args.steps)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop(*span) if rank == 0 else None
-    for _ in range(2):
-        step_e2e()
-    ms_e2e, scores_e2e, _, _ = timed(step_e2e, args.steps)
-    assert all(np.array_equal(a, b) for a, b in zip(scores, scores_e2e)), "resident and e2e legs disagree"
+    if args.no_e2e:
+        ms_e2e = None
+    else:
+        for _ in range(2):
+            step_e2e()
+        ms_e2e, scores_e2e, _, _ = timed(step_e2e, args.steps)
+        assert all(np.array_equal(a, b) for a, b in zip(scores, scores_e2e)), "resident and e2e legs disagree"
 
     # roofline of the dominant kernel (counting): algorithmic HSET2 lane-ops / measured kernel time vs the live-measured
     # HSET2 issue rate of this GPU (the pipe the kernel is bound by)
@@ -301,9 +321,10 @@ def main():
         "dtype": "f16x2 compares of exact small integers -> u16x2 integer counters, u16 table, f64 scores", "data": "synthetic",
         "config": {"workload": f"{wname}: {w['label']}", "seed": w["seed"], "quartets": nq, "trees": m,
                    "l2": "inputs larger than L2: the distance matrices (%.0f MB) are rebuilt and re-streamed every step" % (2e-6 * n * ((n + 7) // 8 * 8) * m),
-                   "parallelism": f"rank-space shards x{world}"},
-        "e2e": {"value": nq * m * args.steps / (ms_e2e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e2e / args.steps,
-                "h2d_bytes_per_step": int(h_off.numel() * 8 + h_par.numel() * 4 + h_leaf.numel() * 4), "d2h_bytes_per_step": int(3 * E * 8)},
+                   "parallelism": f"rank-space shards x{world}", "table": "table-free slabs (counted, scanned, discarded)" if table_free else "resident in HBM"},
+        "e2e": None if args.no_e2e else {
+            "value": nq * m * args.steps / (ms_e2e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e2e / args.steps,
+            "h2d_bytes_per_step": int(h_off.numel() * 8 + h_par.numel() * 4 + h_leaf.numel() * 4), "d2h_bytes_per_step": int(3 * E * 8)},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -145,6 +145,34 @@ int qs_get_distances(qs_ctx* ctx, int64_t tree, uint16_t* out);
  * single shard only. */
 int qs_write_raw_qic(qs_ctx* ctx, int count_scale, const char* const* taxon_names, const char* path);
 
+/* ---- host ingest -------------------------------------------------------------------------
+ * Replaces: the two serial genesis parses of the evaluation-tree file (src/QuartetScores.cpp:23-32
+ * countEvalTrees, src/QuartetCounterLookup.hpp:202-221 NewickInputIterator loop + the per-tree Euler leaf list,
+ * :207-219) by ONE multi-threaded pass from Newick text straight to the qs_add_trees encoding.  taxon_names[id]
+ * is the label of lookup id `id` (n_taxa entries, the reference tree's leaves left to right).  An evaluation-tree
+ * taxon that is not among them fails with QS_E_TREE and a message naming it (the reference throws
+ * std::out_of_range there, QuartetCounterLookup.hpp:218).  n_threads <= 0: all host cores.  The result does not
+ * depend on the thread count.  No GPU and no context needed for qs_newick_flatten. */
+typedef struct qs_flat_trees qs_flat_trees;
+int qs_newick_flatten(const char* text, size_t text_len, int n_taxa, const char* const* taxon_names, int n_threads,
+                      qs_flat_trees** out, char* errbuf, size_t errbuf_len);
+int qs_flat_trees_view(const qs_flat_trees* f, int64_t* n_trees, int64_t* n_nodes, const int64_t** node_offsets,
+                       const int32_t** parent, const int32_t** leaf_lookup_id);
+void qs_flat_trees_free(qs_flat_trees* f);
+/* flatten + qs_add_trees in one call, from memory or from a file (read whole; one tree or many, ';'-terminated) */
+int qs_add_newick(qs_ctx* ctx, const char* text, size_t text_len, const char* const* taxon_names, int n_threads, int64_t* n_trees_added);
+int qs_add_newick_file(qs_ctx* ctx, const char* path, const char* const* taxon_names, int n_threads, int64_t* n_trees_added);
+
+/* ---- table persistence -------------------------------------------------------------------
+ * The reference keeps its table only in RAM (the STXXL external-memory idea is commented out,
+ * src/quartet_lookup_table.hpp:3,218-222).  qs_save_table writes this shard's counted table (QS_MODE_TABLE, after
+ * qs_count) to `path`: a 64-byte header {magic "QSTBL001", n_taxa, cint_bytes, n_trees, s3_begin, s3_end,
+ * rank_begin, rank_end} followed by the entries in QuartetLookupTable layout.  qs_load_table restores it into a
+ * context created with the same n_taxa / cint_bytes / shard, which can then score against any reference tree
+ * on the same taxon ids without recounting. */
+int qs_save_table(qs_ctx* ctx, const char* path);
+int qs_load_table(qs_ctx* ctx, const char* path);
+
 /* Device timing of the last qs_count / scoring pass (CUDA events on the context's stream), and the
  * number of kernels this library launched since the context was created. */
 int qs_last_timing(const qs_ctx* ctx, double* dist_ms, double* count_ms, double* score_ms);
@@ -152,7 +180,7 @@ int qs_launch_count(const qs_ctx* ctx, int64_t* n_launches);
 
 /* Tree classes found by the last qs_count: class A = gene trees that contain all n taxa and have no node of
  * degree > 3, so they resolve every quartet and need two compares per quartet instead of three
- * (kernels/count_items.cuh).  Reported so that bench.py can state the algorithmic work of a run. */
+ * (kernels/count_rows.cuh).  Reported so that bench.py can state the algorithmic work of a run. */
 int qs_tree_classes(const qs_ctx* ctx, int64_t* n_class_a, int64_t* n_class_b);
 
 /* Live micro-benchmark of the issue rate the counting kernel is bound by: packed fp16x2 compare

@@ -3,8 +3,8 @@
 //
 // Same template name, constructor arguments and methods as the reference class, so the reference's own
 // main (src/QuartetScores.cpp:114-147) compiles against it unchanged — see integration/main_b200.cpp and
-// INTEGRATION.md.  Host side only: genesis still parses the Newick files and numbers nodes/edges, this class
-// flattens the trees and hands them to the GPU library.  All counting and scoring happens
+// INTEGRATION.md.  Host side only: genesis still parses the REFERENCE tree and numbers its nodes/edges (the annotated-Newick writer
+// depends on that numbering); the evaluation trees go through libqscuda's parallel single-pass parser.  All counting and scoring happens
 // in libqscuda.so; there is no CPU fallback (a missing GPU is a std::runtime_error).
 //
 // Multi-GPU: one process, one context per visible device (or $QS_NUM_GPUS), each owning a shard of the quartet
@@ -134,29 +134,31 @@ QuartetScoreComputer<CINT>::QuartetScoreComputer(Tree const& refTree, const std:
                                            ref.first_child.data(), ref.next_sibling.data()), "qs_set_reference");
     }
 
-    // stream the evaluation trees: parse (genesis), flatten, hand over in batches
+    // evaluation trees: one multi-threaded pass from the Newick text to the flat encoding (libqscuda's own parser,
+    // qs_newick_flatten) instead of a second serial genesis parse (QuartetCounterLookup.hpp:202-221); an unknown taxon
+    // is reported where the reference throws std::out_of_range (:218)
     std::chrono::steady_clock::time_point begin = std::chrono::steady_clock::now();
     {
-        utils::InputStream instream(utils::make_unique<utils::FileInputSource>(evalTreesPath));
-        DefaultTreeNewickReader reader;                        // kept alive: the iterator's reader copy refers to its plugin
-        auto itTree = NewickInputIterator(instream, reader);
-        std::vector<int64_t> off{0};
-        std::vector<int32_t> par, leaf;
-        FlatTree ft;
-        auto flush = [&]() {
-            if (off.size() <= 1) return;
-            for (auto c : ctxs) qs_check(c, qs_add_trees(c, (int)off.size() - 1, off.data(), par.data(), leaf.data()), "qs_add_trees");
-            off.assign(1, 0); par.clear(); leaf.clear();
-        };
-        while (itTree) {
-            flatten_tree(*itTree, ft, false, &nameToId, nullptr);
-            par.insert(par.end(), ft.parent.begin(), ft.parent.end());
-            leaf.insert(leaf.end(), ft.leaf_id.begin(), ft.leaf_id.end());
-            off.push_back((int64_t)par.size());
-            if (par.size() > (size_t(1) << 22)) flush();
-            ++itTree;
+        std::string text = utils::file_read(evalTreesPath);
+        std::vector<const char*> names;
+        for (auto const& t : taxa) names.push_back(t.c_str());
+        qs_flat_trees* flat = nullptr;
+        char err[512] = {0};
+        int threads = 0;
+        if (const char* env = std::getenv("OMP_NUM_THREADS")) threads = std::atoi(env);
+        const int rc = qs_newick_flatten(text.data(), text.size(), n, names.data(), threads, &flat, err, sizeof err);
+        if (rc != QS_OK) {
+            if (std::string(err).find("is not in the reference tree") != std::string::npos) throw std::out_of_range(std::string("unordered_map::at: ") + err);
+            throw std::runtime_error(std::string("evaluation trees: ") + err);
         }
-        flush();
+        int64_t T = 0, N = 0;
+        const int64_t* off = nullptr; const int32_t *par = nullptr, *leaf = nullptr;
+        qs_flat_trees_view(flat, &T, &N, &off, &par, &leaf);
+        for (auto c : ctxs) {
+            const int r = qs_add_trees(c, (int)T, off, par, leaf);
+            if (r != QS_OK) { qs_flat_trees_free(flat); qs_check(c, r, "qs_add_trees"); }
+        }
+        qs_flat_trees_free(flat);
     }
     std::cout << "Finished parsing evaluation trees.\n";
 

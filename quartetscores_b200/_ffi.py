@@ -46,6 +46,13 @@ SIGNATURES = {
     "qs_plan_stats": (C.c_int, [C.c_int, C.c_int, C.c_int, _i64p]),
     "qs_get_distances": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint16)]),
     "qs_write_raw_qic": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_char_p]),
+    "qs_newick_flatten": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
+    "qs_flat_trees_view": (C.c_int, [C.c_void_p, _i64p, _i64p, C.POINTER(_i64p), C.POINTER(_i32p), C.POINTER(_i32p)]),
+    "qs_flat_trees_free": (None, [C.c_void_p]),
+    "qs_add_newick": (C.c_int, [C.c_void_p, C.c_char_p, C.c_size_t, C.POINTER(C.c_char_p), C.c_int, _i64p]),
+    "qs_add_newick_file": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_char_p), C.c_int, _i64p]),
+    "qs_save_table": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "qs_load_table": (C.c_int, [C.c_void_p, C.c_char_p]),
     "qs_last_timing": (C.c_int, [C.c_void_p, _f64p, _f64p, _f64p]),
     "qs_launch_count": (C.c_int, [C.c_void_p, _i64p]),
     "qs_tree_classes": (C.c_int, [C.c_void_p, _i64p, _i64p]),

@@ -93,6 +93,26 @@ class Context:
         self._check(self._lib.qs_add_trees(self._h, n_trees, C.cast(off_ptr, C.POINTER(C.c_int64)), C.cast(parent_ptr, C.POINTER(C.c_int32)),
                                            C.cast(leaf_ptr, C.POINTER(C.c_int32))), "qs_add_trees")
 
+    def add_newick(self, text: Union[str, bytes], taxa: Sequence[str], n_threads: int = 0) -> int:
+        """Native single-pass parallel ingest (csrc/ingest.cpp): Newick text -> device, returns the trees added."""
+        data = text.encode() if isinstance(text, str) else text
+        arr = (C.c_char_p * len(taxa))(*[t.encode() for t in taxa])
+        got = C.c_int64()
+        self._check(self._lib.qs_add_newick(self._h, data, len(data), arr, n_threads, C.byref(got)), "qs_add_newick")
+        return got.value
+
+    def add_newick_file(self, path: str, taxa: Sequence[str], n_threads: int = 0) -> int:
+        arr = (C.c_char_p * len(taxa))(*[t.encode() for t in taxa])
+        got = C.c_int64()
+        self._check(self._lib.qs_add_newick_file(self._h, path.encode(), arr, n_threads, C.byref(got)), "qs_add_newick_file")
+        return got.value
+
+    def save_table(self, path: str):
+        self._check(self._lib.qs_save_table(self._h, path.encode()), "qs_save_table")
+
+    def load_table(self, path: str):
+        self._check(self._lib.qs_load_table(self._h, path.encode()), "qs_load_table")
+
     def clear_trees(self):
         self._check(self._lib.qs_clear_trees(self._h), "qs_clear_trees")
 
@@ -173,6 +193,29 @@ class Context:
         return a.value, b.value
 
 
+def flatten_newick_native(text: Union[str, bytes], taxa: Sequence[str], n_threads: int = 0) -> FlatTrees:
+    """Newick text -> FlatTrees through the library's parallel parser (qs_newick_flatten; no GPU, no context).
+    Same arrays as newick.flatten_eval_trees(parse_newick_many(text), taxa); an unknown taxon raises QSError."""
+    lib = _ffi.load()
+    data = text.encode() if isinstance(text, str) else text
+    arr = (C.c_char_p * len(taxa))(*[t.encode() for t in taxa])
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib.qs_newick_flatten(data, len(data), len(taxa), arr, n_threads, C.byref(h), err, len(err))
+    if rc != 0:
+        raise _ffi.QSError(rc, "qs_newick_flatten: " + err.value.decode(errors="replace"))
+    try:
+        T, N = C.c_int64(), C.c_int64()
+        po, pp, pl = C.POINTER(C.c_int64)(), C.POINTER(C.c_int32)(), C.POINTER(C.c_int32)()
+        lib.qs_flat_trees_view(h, C.byref(T), C.byref(N), C.byref(po), C.byref(pp), C.byref(pl))
+        off = np.ctypeslib.as_array(po, shape=(T.value + 1,)).copy()
+        par = np.ctypeslib.as_array(pp, shape=(N.value,)).copy() if N.value else np.empty(0, np.int32)
+        leaf = np.ctypeslib.as_array(pl, shape=(N.value,)).copy() if N.value else np.empty(0, np.int32)
+    finally:
+        lib.qs_flat_trees_free(h)
+    return FlatTrees(off, par, leaf)
+
+
 class QuartetScoreComputer:
     """Mirror of ``QuartetScoreComputer<CINT>`` (src/QuartetScoreComputer.hpp:43-51).
 
@@ -194,9 +237,11 @@ class QuartetScoreComputer:
                 with open(text) as f:
                     text = f.read()
             try:
-                flat = flatten_eval_trees(parse_newick_many(text), self.ref.taxa)
-            except KeyError as e:          # reference: std::out_of_range from unordered_map::at (QuartetCounterLookup.hpp:218)
-                raise IndexError(f"unordered_map::at: taxon {e} of an evaluation tree is not in the reference tree") from None
+                flat = flatten_newick_native(text, self.ref.taxa)
+            except _ffi.QSError as e:      # reference: std::out_of_range from unordered_map::at (QuartetCounterLookup.hpp:218)
+                if "is not in the reference tree" in str(e):
+                    raise IndexError(f"unordered_map::at: {e}") from None
+                raise
         self.m = flat.n_trees if m is None else m
         self.savemem = savemem
         self.cint_bytes = cint_bytes_for(self.m)

@@ -1007,6 +1007,113 @@ int qs_get_counts(qs_ctx* ctx, uint64_t rank_begin, uint64_t rank_end, void* out
     return QS_OK;
 }
 
+// ---- host ingest: Newick text -> qs_add_trees (parser in ingest.cpp) -------------------------------------------
+int qs_add_newick(qs_ctx* ctx, const char* text, size_t text_len, const char* const* taxon_names, int n_threads, int64_t* n_trees_added) {
+    if (!ctx || (!text && text_len) || !taxon_names) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
+    qs_flat_trees* f = nullptr;
+    char eb[400];
+    eb[0] = 0;
+    int r = qs_newick_flatten(text, text_len, ctx->n, taxon_names, n_threads, &f, eb, sizeof eb);
+    if (r) QS_FAIL(ctx, r, "%s", eb);
+    int64_t T = 0, N = 0;
+    const int64_t* off; const int32_t *par, *leaf;
+    qs_flat_trees_view(f, &T, &N, &off, &par, &leaf);
+    if (T > 0x7fffffffLL) { qs_flat_trees_free(f); QS_FAIL(ctx, QS_E_UNSUPPORTED, "too many trees"); }
+    r = qs_add_trees(ctx, (int)T, off, par, leaf);
+    qs_flat_trees_free(f);
+    if (r == QS_OK && n_trees_added) *n_trees_added = T;
+    return r;
+}
+
+int qs_add_newick_file(qs_ctx* ctx, const char* path, const char* const* taxon_names, int n_threads, int64_t* n_trees_added) {
+    if (!ctx || !path || !taxon_names) return QS_E_ARG;
+    FILE* fp = fopen(path, "rb");
+    if (!fp) QS_FAIL(ctx, QS_E_ARG, "cannot open %s", path);
+    std::string buf;
+    char chunk[1 << 16];
+    size_t got;
+    while ((got = fread(chunk, 1, sizeof chunk, fp)) > 0) buf.append(chunk, got);
+    fclose(fp);
+    return qs_add_newick(ctx, buf.data(), buf.size(), taxon_names, n_threads, n_trees_added);
+}
+
+// ---- table persistence ------------------------------------------------------------------------------------------
+namespace {
+struct TableHeader {
+    char magic[8];
+    int32_t n_taxa, cint_bytes;
+    int64_t n_trees;
+    int32_t s3_begin, s3_end;
+    uint64_t rank_begin, rank_end;
+    uint64_t reserved[2];
+};
+static_assert(sizeof(TableHeader) == 64, "table file header is 64 bytes");
+constexpr size_t kIoChunk = (size_t)64 << 20;
+}  // namespace
+
+int qs_save_table(qs_ctx* ctx, const char* path) {
+    if (!ctx || !path) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
+    if (ctx->mode != QS_MODE_TABLE) QS_FAIL(ctx, QS_E_STATE, "table-free context keeps no table");
+    if (!ctx->counted) QS_FAIL(ctx, QS_E_STATE, "qs_count has not been called");
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    FILE* fp = fopen(path, "wb");
+    if (!fp) QS_FAIL(ctx, QS_E_ARG, "cannot create %s", path);
+    TableHeader h{};
+    memcpy(h.magic, "QSTBL001", 8);
+    h.n_taxa = ctx->n; h.cint_bytes = ctx->cint_bytes; h.n_trees = ctx->m; h.s3_begin = ctx->d_begin; h.s3_end = ctx->d_end;
+    h.rank_begin = ctx->rank_begin; h.rank_end = ctx->rank_end;
+    bool ok = fwrite(&h, sizeof h, 1, fp) == 1;
+    const size_t total = (size_t)(ctx->rank_end - ctx->rank_begin) * 3 * ctx->cint_bytes;
+    std::vector<char> buf(std::min(total, kIoChunk));
+    for (size_t o = 0; ok && o < total; o += kIoChunk) {
+        const size_t len = std::min(kIoChunk, total - o);
+        cudaError_t e = cudaMemcpyAsync(buf.data(), (const char*)ctx->d_table + o, len, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { fclose(fp); QS_CUDA(ctx, e); }
+        ok = fwrite(buf.data(), 1, len, fp) == len;
+    }
+    ok = (fclose(fp) == 0) && ok;
+    if (!ok) QS_FAIL(ctx, QS_E_ARG, "short write to %s", path);
+    return QS_OK;
+}
+
+int qs_load_table(qs_ctx* ctx, const char* path) {
+    if (!ctx || !path) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
+    if (ctx->mode != QS_MODE_TABLE) QS_FAIL(ctx, QS_E_STATE, "table-free context keeps no table");
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    FILE* fp = fopen(path, "rb");
+    if (!fp) QS_FAIL(ctx, QS_E_ARG, "cannot open %s", path);
+    TableHeader h{};
+    if (fread(&h, sizeof h, 1, fp) != 1 || memcmp(h.magic, "QSTBL001", 8) != 0) { fclose(fp); QS_FAIL(ctx, QS_E_ARG, "%s is not a qscuda table file", path); }
+    if (h.n_taxa != ctx->n || h.cint_bytes != ctx->cint_bytes || h.s3_begin != ctx->d_begin || h.s3_end != ctx->d_end || h.rank_begin != ctx->rank_begin ||
+        h.rank_end != ctx->rank_end) {
+        fclose(fp);
+        QS_FAIL(ctx, QS_E_ARG, "%s holds %d taxa, %d-byte counters, s3 in [%d,%d); this context has %d taxa, %d-byte counters, s3 in [%d,%d)", path, h.n_taxa,
+                h.cint_bytes, h.s3_begin, h.s3_end, ctx->n, ctx->cint_bytes, ctx->d_begin, ctx->d_end);
+    }
+    const size_t total = (size_t)(ctx->rank_end - ctx->rank_begin) * 3 * ctx->cint_bytes;
+    if (total > ctx->table_bytes) {
+        if (ctx->d_table) { cudaFree(ctx->d_table); ctx->d_table = nullptr; ctx->table_bytes = 0; }
+        cudaError_t e = cudaMalloc(&ctx->d_table, total);
+        if (e != cudaSuccess) { cudaGetLastError(); fclose(fp); QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! count table of %zu bytes does not fit this device", total); }
+        ctx->table_bytes = total;
+    }
+    std::vector<char> buf(std::min(total, kIoChunk));
+    for (size_t o = 0; o < total; o += kIoChunk) {
+        const size_t len = std::min(kIoChunk, total - o);
+        if (fread(buf.data(), 1, len, fp) != len) { fclose(fp); QS_FAIL(ctx, QS_E_ARG, "%s is truncated", path); }
+        cudaError_t e = cudaMemcpyAsync((char*)ctx->d_table + o, buf.data(), len, cudaMemcpyHostToDevice, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { fclose(fp); QS_CUDA(ctx, e); }
+    }
+    fclose(fp);
+    ctx->counted = true;          // scoring / qs_get_counts may follow without qs_count
+    return QS_OK;
+}
+
 int qs_get_distances(qs_ctx* ctx, int64_t tree, uint16_t* out) {
     if (!ctx || !out) return QS_E_ARG;
     if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");

@@ -51,16 +51,16 @@ def _tokenize(text: str) -> Iterator[tuple]:
             if j < 0:
                 raise NewickError("unterminated comment")
             i = j + 1                       # comments are dropped (the reference ignores them)
-        elif ch == "'":
+        elif ch in "'\"":                   # genesis reader.cpp:371-373: either quote, a doubled quote stands for itself
             j = i + 1
             out = []
             while True:
-                k = text.find("'", j)
+                k = text.find(ch, j)
                 if k < 0:
                     raise NewickError("unterminated quoted label")
                 out.append(text[j:k])
-                if k + 1 < n and text[k + 1] == "'":
-                    out.append("'")
+                if k + 1 < n and text[k + 1] == ch:
+                    out.append(ch)
                     j = k + 2
                 else:
                     i = k + 1
@@ -68,7 +68,7 @@ def _tokenize(text: str) -> Iterator[tuple]:
             yield ("label", "".join(out))
         else:
             j = i
-            while j < n and not text[j].isspace() and text[j] not in "(),:;[]'":
+            while j < n and not text[j].isspace() and text[j] not in "(),:;[]":
                 j += 1
             yield ("label", text[i:j])
             i = j

@@ -101,7 +101,8 @@ def _in_subtree(t: _T, node: int, top: int) -> bool:
 
 def spr_move(t: _T, rng: random.Random, nni: bool = False) -> None:
     """One random subtree-prune-and-regraft (or NNI) that keeps the root node in place."""
-    nodes = [v for v in t.live_nodes() if v != t.root and t.parent[v] != t.root]
+    live = t.live_nodes()
+    nodes = [v for v in live if v != t.root and t.parent[v] != t.root]
     if not nodes:
         return
     for _ in range(20):
@@ -111,11 +112,17 @@ def spr_move(t: _T, rng: random.Random, nni: bool = False) -> None:
         if len(t.children[p]) != 2:
             continue
         sib = t.children[p][0] if t.children[p][1] == x else t.children[p][1]
+        sub = set()                                # nodes of the pruned subtree (one DFS instead of a root walk per candidate)
+        st = [x]
+        while st:
+            v = st.pop()
+            sub.add(v)
+            st.extend(t.children[v])
         if nni:
             cands = [c for c in t.children[g] if c != p] + ([g] if g != t.root else [])
         else:
-            cands = [v for v in t.live_nodes() if v != t.root and v != p and v != sib and not _in_subtree(t, v, x)]
-        cands = [v for v in cands if v != t.root and not _in_subtree(t, v, x) and v != p]
+            cands = [v for v in live if v != t.root and v != p and v != sib and v not in sub]
+        cands = [v for v in cands if v != t.root and v not in sub and v != p]
         if not cands:
             continue
         y = rng.choice(cands)

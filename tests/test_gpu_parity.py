@@ -255,3 +255,42 @@ def test_mixed_tree_classes_and_odd_counts():
     ctx.close()
     want = (O.count_clades_compact(26, a.flat) + O.count_clades_compact(26, b.flat)) // 2
     assert np.array_equal(got, want)
+
+
+# ---- native ingest and table persistence -------------------------------------------------
+
+@pytest.mark.parametrize("name", golden_cases())
+def test_golden_counts_through_native_newick_ingest(name, golden, tmp_path):
+    """Newick text -> qs_add_newick(_file) -> counts: the reference's golden table, without the Python parser."""
+    g = golden(name)
+    _, ref, flat = load_input(g)
+    bits = cint_bits_for(flat.n_trees)
+    p = tmp_path / "eval.nwk"
+    p.write_text(g["eval_newick"])
+    for use_file in (False, True):
+        with Context(ref.n_taxa, bits // 8) as ctx:
+            ctx.set_reference(ref)
+            got = ctx.add_newick_file(str(p), ref.taxa, 3) if use_file else ctx.add_newick(g["eval_newick"], ref.taxa, 2)
+            assert got == flat.n_trees == ctx.num_trees()
+            ctx.count()
+            assert np.array_equal(ctx.get_counts().astype(np.uint32), g["counts"].astype(np.uint32))
+
+
+def test_table_save_load_roundtrip(tmp_path):
+    s = SyntheticInput(30, 400, seed=21, k_max=8, p_missing=0.1, p_contract=0.1, want_newick=False)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    path = str(tmp_path / "table.qstbl")
+    with run_ctx(ref, s.flat) as ctx:
+        table = ctx.get_counts()
+        scores = ctx.score(1)
+        ctx.save_table(path)
+    assert os.path.getsize(path) == 64 + table.nbytes
+    with Context(ref.n_taxa, 2) as ctx:                    # a fresh context: no trees, no counting
+        ctx.set_reference(ref)
+        ctx.load_table(path)
+        assert np.array_equal(ctx.get_counts(), table)
+        for a, b in zip(ctx.score(1), scores):
+            assert np.array_equal(a, b)
+    with Context(ref.n_taxa, 1) as ctx:                    # wrong counter width is refused
+        with pytest.raises(Exception):
+            ctx.load_table(path)
