@@ -52,6 +52,19 @@ TABLE_BYTES_LIMIT = 120e9      # a shard's uint16 table above this is not kept r
 # tree (class B) needs 3 = 1.5.
 HSET2_LANEOPS_PER_EVAL = {"A": 1.0, "B": 1.5}
 INT32_LANEOPS_PER_EVAL = 9.0       # 3 adds + 3 compares + 3 predicated increments
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the counting kernel from the committed `ncu --set full`
+# capture of the same workload on one GPU (profiles/r01_g_count_rows_cfg2_ncu_full.txt: 384.9 MB + 88.6 MB); null where
+# no capture of that exact workload exists
+NCU_DRAM_TRAFFIC_BYTES = {("cfg2", 1): 384936960 + 88566272}
+
+
+def hbm_peak_gbs():
+    """Measured HBM copy bandwidth of this pool's B200s (driver-written MEASURED_PEAKS.json), else the profiling guide's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0      # B200_PROFILING.md fallback ("of fallback")
 
 
 def make_input(w, want_newick=False):
@@ -300,19 +313,26 @@ def main():
     my_quartets = r1 - r0
     my_evals = my_quartets * m
     algo_laneops = my_quartets * (nA * HSET2_LANEOPS_PER_EVAL["A"] + nB * HSET2_LANEOPS_PER_EVAL["B"])
+    per_rank_ms = None
+    if dist is not None:      # the counting kernel's time on every rank: shows how even the rank-space shards are
+        g = [torch.zeros(3, device="cuda", dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(g, torch.tensor([count_ms, statistics.mean(t["dist_ms"] for t in kt), statistics.mean(t["score_ms"] for t in kt)], device="cuda", dtype=torch.float64))
+        per_rank_ms = [[round(float(v), 3) for v in x.tolist()] for x in g]
     achieved = algo_laneops / (count_ms * 1e-3)
     roofline = {
         "bound": "alu_issue", "achieved": achieved / 1e12, "peak": hset2_peak / 1e12, "unit": "Tlaneop/s", "frac": achieved / hset2_peak,
-        "traffic": None,
+        "traffic": NCU_DRAM_TRAFFIC_BYTES.get((wname, world)),
         "kernel": "qs_count_rows_kernel", "kernel_ms": count_ms,
         "dist_kernel_ms": statistics.mean(t["dist_ms"] for t in kt), "score_kernel_ms": statistics.mean(t["score_ms"] for t in kt),
         "peak_source": "measured live on this GPU: HSET2 (fp16x2 compare -> mask) lane-op rate in the kernel's own 2xHSET2+IADD3 mix (qs_measure_alu_peak)",
         "algorithmic_laneops_per_eval": algo_laneops / my_evals,
         "tree_classes": {"A_fully_resolved": nA, "B_general": nB},
+        "per_rank_ms[count,dist,score]": per_rank_ms,
         "int32_equiv": {"achieved": INT32_LANEOPS_PER_EVAL * my_evals / (count_ms * 1e-3) / 1e12, "peak": int32_peak / 1e12, "unit": "Tlaneop/s",
                         "frac": INT32_LANEOPS_PER_EVAL * my_evals / (count_ms * 1e-3) / int32_peak,
                         "note": "SURVEY §8d accounting: 9 scalar int32 lane-ops per evaluation vs the measured INT32 (LOP3/IADD3) lane rate"},
-        "hbm": {"algorithmic_bytes": (r1 - r0) * 6 + 2 * n * n * m, "note": "table written once + distance matrices read once; the path is ALU-bound by three orders of magnitude"},
+        "hbm": {"algorithmic_bytes": (r1 - r0) * 6 + 2 * n * n * m, "achieved_gbs": ((r1 - r0) * 6 + 2 * n * n * m) / (count_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak_gbs(),
+                "note": "table written once + distance matrices read once; the path is ALU-bound by three orders of magnitude (traffic = ncu DRAM bytes of one launch)"},
     }
 
     line = {

@@ -142,14 +142,40 @@ struct RowPipe {
     uint32_t phase;             // bit s = parity to wait for on full[s]
 };
 
-// Stream the trees [t0,t1) of the class-sorted order through the pipeline, trees_per_stage at a time.  Per tree,
-// ld(base) fetches the thread's operands from the staged rows at `base` and mt(operands) does the compares; with
-// PF the operands of the next tree of the stage are fetched before the math of the current one (the LDS latency
-// otherwise shows up as a short-scoreboard stall at the top of every tree: profiles/r01_e_*).  Warps run
+// Stream the trees [t0,t1) of the class-sorted order through the pipeline, up to CR_MAX_TPS trees per stage; stage(base, nt,
+// slot) runs the caller's tree loop over the nt trees staged at base, base + slot, ...  Warps run
 // independently: the last warp to finish a stage refills it (no CTA-wide barrier inside the loop).  The chunk's tree
 // ids are copied to shared memory once per task, so no warp waits on global memory inside the loop.
-template <bool PF, class LD, class MT>
-__device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, const RowTask& T, int t0, int t1, LD&& ld, MT&& mt) {
+// per-stage tree loops.  stage_pf: one operand set per tree, the next tree's operands are fetched before the math of the
+// current one (the LDS latency otherwise shows up as a short-scoreboard stall at the top of every tree: profiles/r01_e_*).
+// stage_halves: two half-cost items per thread (role Y); the operands of item B are in flight during the math of item A
+// and those of the next tree's item A during the math of item B — same register footprint as stage_pf.
+template <class LD, class MT>
+__device__ __forceinline__ void stage_pf(const unsigned char* base, int nt, uint32_t slot, LD&& ld, MT&& mt) {
+    auto cur = ld(base);
+#pragma unroll 1
+    for (int tt = 0; tt < nt; ++tt) {
+        if (tt + 1 < nt) base += slot;               // (the last tree of a stage re-reads itself: no branch around the loads)
+        auto nx = ld(base);
+        mt(cur);
+        cur = nx;
+    }
+}
+template <class LDA, class LDB, class MTA, class MTB>
+__device__ __forceinline__ void stage_halves(const unsigned char* base, int nt, uint32_t slot, LDA&& lda, LDB&& ldb, MTA&& mta, MTB&& mtb) {
+    auto ca = lda(base);
+#pragma unroll 1
+    for (int tt = 0; tt < nt; ++tt) {
+        auto cb = ldb(base);
+        mta(ca);
+        if (tt + 1 < nt) base += slot;
+        ca = lda(base);
+        mtb(cb);
+    }
+}
+
+template <class STAGE>
+__device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, const RowTask& T, int t0, int t1, STAGE&& stage) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int ntrees = t1 - t0;
     const size_t tree_elems = (size_t)a.n * a.n_pad;
@@ -189,20 +215,7 @@ __device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, 
         mbar_wait(&P.full[buf], (P.phase >> buf) & 1u);
         P.phase ^= (1u << buf);
         const int nt = min(tps, ntrees - st * tps);
-        const unsigned char* base = P.bufs + (size_t)buf * stage_bytes;
-        if (PF) {
-            auto cur = ld(base);
-#pragma unroll 1
-            for (int tt = 0; tt < nt; ++tt) {
-                if (tt + 1 < nt) base += slot;               // (the last tree of a stage re-reads itself: no branch around the loads)
-                auto nx = ld(base);
-                mt(cur);
-                cur = nx;
-            }
-        } else {
-#pragma unroll 1
-            for (int tt = 0; tt < nt; ++tt, base += slot) mt(ld(base));
-        }
+        stage(P.bufs + (size_t)buf * stage_bytes, nt, slot);
         __syncwarp();
         int last = 0;
         if (lane == 0) last = (atomicAdd(&P.done[buf], 1) == CR_THREADS / 32 - 1);
@@ -280,9 +293,11 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
             const uint32_t rp = valid ? cr_row_off(T, c, rb) : 0u, rq = valid ? cr_row_off(T, d, rb) : 0u;
             const uint32_t oPu = rp + ia * 16u, oQu = rq + ia * 16u, oPv = rp + ib * 16u, oQv = rq + ib * 16u;
             XCounters x; zero(x);
-            stream_rows<true>(a, P, T, t0, t1,
-                [&](const unsigned char* s) { return BlockRows{lds128(s, oPu), lds128(s, oQu), lds128(s, oPv), lds128(s, oQv)}; },
-                [&](const BlockRows& r) { step_gt_lt(x, r); });
+            stream_rows(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
+                stage_pf(base, nt, slot,
+                         [&](const unsigned char* s) { return BlockRows{lds128(s, oPu), lds128(s, oQu), lds128(s, oPv), lds128(s, oQv)}; },
+                         [&](const BlockRows& r) { step_gt_lt(x, r); });
+            });
             if (valid) {
                 const uint64_t rcd = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
 #pragma unroll
@@ -312,9 +327,11 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
             const uint32_t oAp = (vA ? cr_row_off(T, cA, rb) : 0u) + jA * 16u, oAq = (vA ? cr_row_off(T, dA, rb) : 0u) + jA * 16u;
             const uint32_t oBp = (vB ? cr_row_off(T, cB, rb) : 0u) + jB * 16u, oBq = (vB ? cr_row_off(T, dB, rb) : 0u) + jB * 16u;
             GCounters ga, gb; zero(ga); zero(gb);
-            stream_rows<true>(a, P, T, t0, t1,
-                [&](const unsigned char* s) { return BlockRows{lds128(s, oAp), lds128(s, oAq), lds128(s, oBp), lds128(s, oBq)}; },
-                [&](const BlockRows& r) { step_gt_diag(ga, r.pu, r.qu); step_gt_diag(gb, r.pv, r.qv); });
+            stream_rows(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
+                stage_pf(base, nt, slot,
+                         [&](const unsigned char* s) { return BlockRows{lds128(s, oAp), lds128(s, oAq), lds128(s, oBp), lds128(s, oBq)}; },
+                         [&](const BlockRows& r) { step_gt_diag(ga, r.pu, r.qu); step_gt_diag(gb, r.pv, r.qv); });
+            });
             auto flush = [&](int c, int d, int blk, const GCounters& g) {
                 const int x0 = blk * 8;
                 const uint64_t rcd = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
@@ -349,13 +366,12 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
             const uint32_t oApu = pA + iaA * 16u, oAqu = qA + iaA * 16u, oApv = pA + idA * 16u, oAqv = qA + idA * 16u;
             const uint32_t oBpu = pB + iaB * 16u, oBqu = qB + iaB * 16u, oBpv = pB + idB * 16u, oBqv = qB + idB * 16u;
             GCounters ga, gb; zero(ga); zero(gb);
-            struct TwoBlocks { BlockRows a, b; };
-            stream_rows<false>(a, P, T, t0, t1,
-                [&](const unsigned char* s) {
-                    return TwoBlocks{BlockRows{lds128(s, oApu), lds128(s, oAqu), lds128(s, oApv), lds128(s, oAqv)},
-                                     BlockRows{lds128(s, oBpu), lds128(s, oBqu), lds128(s, oBpv), lds128(s, oBqv)}};
-                },
-                [&](const TwoBlocks& r) { step_gt(ga, r.a); step_gt(gb, r.b); });
+            stream_rows(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
+                stage_halves(base, nt, slot,
+                             [&](const unsigned char* s) { return BlockRows{lds128(s, oApu), lds128(s, oAqu), lds128(s, oApv), lds128(s, oAqv)}; },
+                             [&](const unsigned char* s) { return BlockRows{lds128(s, oBpu), lds128(s, oBqu), lds128(s, oBpv), lds128(s, oBqv)}; },
+                             [&](const BlockRows& r) { step_gt(ga, r); }, [&](const BlockRows& r) { step_gt(gb, r); });
+            });
             auto flush = [&](int b, int c, int ia, int id, const GCounters& g) {
                 const int dlo = max(c + 1, a.d_begin);
 #pragma unroll

@@ -30,6 +30,7 @@ struct ScoreArgs {
     const uint16_t* idepth;    // [I] depth of inner node (by inner index)
     unsigned long long* pair_sums;   // [I*I][3]
     unsigned long long* pair_best;   // [I*I] packed triple of the min-QIC quartet, ~0 = none
+    int* pair_hint;                  // [I*I] order-preserving int image of an fp32 UPPER bound of the pair's current best score
     const int64_t* PB;         // [n+1] first block of each b
     int n, I;
     int d_begin, d_end;
@@ -47,7 +48,7 @@ __device__ __forceinline__ unsigned long long pack_triple(unsigned long long q1,
 
 // QIC used ON THE DEVICE ONLY TO SELECT the minimum (QuartetScoreComputer.hpp:135-159 restated);
 // reported values are recomputed on the host from the winning triple.
-__device__ __forceinline__ double dev_log_score(unsigned long long q1, unsigned long long q2, unsigned long long q3) {
+__device__ __noinline__ double dev_log_score(unsigned long long q1, unsigned long long q2, unsigned long long q3) {
     const unsigned long long s = q1 + q2 + q3;
     if (s == 0) return 0.0;
     const bool neg = (q1 < q2) || (q1 < q3);
@@ -69,11 +70,60 @@ __device__ __forceinline__ double triple_score(unsigned long long t) {
     return dev_log_score(t >> (2 * QS_TRIPLE_BITS), (t >> QS_TRIPLE_BITS) & M, t & M);
 }
 
+// Selecting the minimum-QIC quartet of a pair WITHOUT an fp64 log_score per quartet.  Every quartet gets an fp32
+// estimate (|estimate - exact| < 1e-5: three p*log2(p) terms of magnitude <= 0.53, each a few fp32 ulps off).  A quartet
+// can be the exact minimum only if its estimate is within QS_FILTER_MARGIN (>= 2 x that error) of the smallest
+// estimate / exact value seen so far, so only those are kept as CANDIDATES (two register slots) and evaluated in fp64
+// when the run ends — at the same loop iteration for all threads of the block (key runs follow lca(a,b), which is
+// block-uniform), so the expensive path is executed converged and ~2 times per run instead of once per quartet.
+constexpr float QS_FILTER_MARGIN = 2e-6f;      // estimate error is < 5e-7 (see dev_log_score_f32)
+// order-preserving float <-> int (so that atomicMin on ints orders floats, negatives included)
+__device__ __forceinline__ int float_to_ordered(float f) { const int b = __float_as_int(f); return b ^ ((b >> 31) & 0x7fffffff); }
+__device__ __forceinline__ float ordered_to_float(int o) { return __int_as_float(o ^ ((o >> 31) & 0x7fffffff)); }
+constexpr int QS_HINT_NONE = 0x7f800000;         // +inf
+__device__ __forceinline__ float dev_log_score_f32(unsigned q1, unsigned q2, unsigned q3) {
+    const unsigned s = q1 + q2 + q3;
+    if (s == 0) return 0.f;
+    const float inv = 1.f / (float)s, il3 = 0.63092975357145743710f;      // 1/log2(3)
+    float acc = 0.f;
+    // __log2f = MUFU.LG2: absolute error <= 2^-22 on [0.5, 2], <= 2 ulp elsewhere, i.e. <= 2.4e-7 per p*log2(p) term and
+    // <= 3e-7 on the estimate; with the fp32 rounding of the rest (2e-7 measured, tests/test_score_filter.py) the estimate is
+    // within 5e-7 of the exact score — a quarter of QS_FILTER_MARGIN
+    if (q1) { const float p = (float)q1 * inv; acc += p * __log2f(p); }
+    if (q2) { const float p = (float)q2 * inv; acc += p * __log2f(p); }
+    if (q3) { const float p = (float)q3 * inv; acc += p * __log2f(p); }
+    const float qic = 1.f + acc * il3;
+    return ((q1 < q2) || (q1 < q3)) ? -qic : qic;
+}
+
 struct PairAcc {
-    unsigned long long s1, s2, s3, best;
-    double best_q;
-    int key;   // pair index or -1
+    unsigned long long s1, s2, s3;
+    unsigned long long best;       // exact champion so far (resolved candidates), QS_TRIPLE_NONE = none
+    double best_q;                 // its exact score
+    unsigned long long cand0, cand1, last_t;
+    float bound;                   // smallest estimate / champion score seen in this run
+    int ncand;
+    int key;                       // pair index or -1
 };
+
+__device__ __forceinline__ void pair_reset(PairAcc& acc) {
+    acc.s1 = acc.s2 = acc.s3 = 0; acc.best = QS_TRIPLE_NONE; acc.best_q = INFINITY; acc.key = -1;
+    acc.cand0 = acc.cand1 = acc.last_t = QS_TRIPLE_NONE; acc.bound = INFINITY; acc.ncand = 0;
+}
+
+// evaluate the pending candidates exactly and fold them into the champion
+__device__ __forceinline__ void pair_resolve(PairAcc& acc) {
+#pragma unroll 1
+    for (int i = 0; i < 2; ++i) {
+        if (i < acc.ncand) {
+            const unsigned long long t = i ? acc.cand1 : acc.cand0;
+            const double q = triple_score(t);
+            if (q < acc.best_q) { acc.best_q = q; acc.best = t; }
+        }
+    }
+    acc.ncand = 0;
+    if (acc.best != QS_TRIPLE_NONE) acc.bound = fminf(acc.bound, (float)acc.best_q);
+}
 
 __device__ __forceinline__ void pair_flush(const ScoreArgs& a, PairAcc& acc) {
     if (acc.key < 0) return;
@@ -81,23 +131,31 @@ __device__ __forceinline__ void pair_flush(const ScoreArgs& a, PairAcc& acc) {
     if (acc.s1) atomicAdd(ps + 0, acc.s1);
     if (acc.s2) atomicAdd(ps + 1, acc.s2);
     if (acc.s3) atomicAdd(ps + 2, acc.s3);
-    if (acc.best != QS_TRIPLE_NONE) {
-        unsigned long long* pb = a.pair_best + acc.key;
-        unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(pb);
-        while (true) {
-            if (!(acc.best_q < triple_score(old))) break;
-            unsigned long long prev = atomicCAS(pb, old, acc.best);
-            if (prev == old) break;
-            old = prev;
+    // pair_hint never lies below the pair's true current minimum (it is lowered only AFTER a successful update of
+    // pair_best, to a value rounded up), so a run whose every quartet is estimated above it cannot improve the pair:
+    // no fp64 evaluation, no CAS.  Most runs end here.
+    const float hint = ordered_to_float(*reinterpret_cast<volatile int*>(a.pair_hint + acc.key));
+    if (acc.bound <= hint + QS_FILTER_MARGIN) {
+        pair_resolve(acc);
+        if (acc.best != QS_TRIPLE_NONE) {
+            unsigned long long* pb = a.pair_best + acc.key;
+            unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(pb);
+            bool won = false;
+            while (true) {
+                if (!(acc.best_q < triple_score(old))) break;
+                unsigned long long prev = atomicCAS(pb, old, acc.best);
+                if (prev == old) { won = true; break; }
+                old = prev;
+            }
+            if (won) atomicMin(a.pair_hint + acc.key, float_to_ordered(__double2float_ru(acc.best_q)));
         }
     }
-    acc.s1 = acc.s2 = acc.s3 = 0; acc.best = QS_TRIPLE_NONE; acc.best_q = INFINITY; acc.key = -1;
+    pair_reset(acc);
 }
 
 // one quartet's contribution; (c0,c1,c2) = table slots after scale/mask
 __device__ __forceinline__ void pair_add(const ScoreArgs& a, PairAcc& acc, int key, int rslot,
-                                         unsigned long long c0, unsigned long long c1, unsigned long long c2,
-                                         unsigned long long& memo_t, double& memo_q) {
+                                         unsigned long long c0, unsigned long long c1, unsigned long long c2) {
     if (key != acc.key) { pair_flush(a, acc); acc.key = key; }
     unsigned long long q1, q2, q3;
     if (rslot == 0) { q1 = c0; q2 = c1; q3 = c2; }
@@ -105,8 +163,21 @@ __device__ __forceinline__ void pair_add(const ScoreArgs& a, PairAcc& acc, int k
     else { q1 = c2; q2 = c0; q3 = c1; }                          // (u,z|v,w): ab|cd, ac|bd = uv|zw, ad|bc = uw|zv
     acc.s1 += q1; acc.s2 += q2; acc.s3 += q3;
     const unsigned long long t = pack_triple(q1, q2, q3);
-    if (t != memo_t) { memo_t = t; memo_q = dev_log_score(q1, q2, q3); }
-    if (memo_q < acc.best_q) { acc.best_q = memo_q; acc.best = t; }
+    if (t == acc.last_t) return;                                 // same counts as the previous quartet: nothing new
+    acc.last_t = t;
+    if ((q1 | q2 | q3) >= (1ull << 24)) {                        // wider than fp32 integers (uint32/uint64 CINT): exact path
+        const double q = dev_log_score(q1, q2, q3);
+        if (q < acc.best_q) { acc.best_q = q; acc.best = t; acc.bound = fminf(acc.bound, (float)q); }
+        return;
+    }
+    const float est = dev_log_score_f32((unsigned)q1, (unsigned)q2, (unsigned)q3);
+    if (est > acc.bound + QS_FILTER_MARGIN) return;              // cannot be the minimum of this run
+    if (est < acc.bound - QS_FILTER_MARGIN) acc.ncand = 0;       // strictly better than everything pending: they are obsolete
+    acc.bound = fminf(acc.bound, est);
+    if ((acc.ncand > 0 && t == acc.cand0) || (acc.ncand > 1 && t == acc.cand1)) return;
+    if (acc.ncand == 2) pair_resolve(acc);                       // both slots taken: settle them exactly, keep the champion
+    if (acc.ncand == 0) acc.cand0 = t; else acc.cand1 = t;
+    acc.ncand++;
 }
 
 // reference topology + pair key of sorted quartet (a,b,c,d) from the three adjacent LCAs (inner indices)
@@ -117,6 +188,10 @@ __device__ __forceinline__ int quartet_pair_key(const ScoreArgs& a, int p, int q
     else if (S2 > S0) { rslot = 2; u = q; v = (dp > dr) ? p : r; }
     else { rslot = -1; return -1; }
     return (u < v) ? u * a.I + v : v * a.I + u;
+}
+
+__global__ void qs_fill_int_kernel(int* __restrict__ p, size_t n, int v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
 template <typename CINT>
@@ -147,18 +222,38 @@ __global__ void __launch_bounds__(128) qs_score_table_kernel(const ScoreArgs a) 
     const CINT* tab = reinterpret_cast<const CINT*>(a.table) + (quartet_rank(0, b, c, d) - a.rank_base) * 3;
     const uint16_t* lrow = a.lca + (size_t)b * a.n;
 
-    PairAcc acc; acc.s1 = acc.s2 = acc.s3 = 0; acc.best = QS_TRIPLE_NONE; acc.best_q = INFINITY; acc.key = -1;
-    unsigned long long memo_t = QS_TRIPLE_NONE; double memo_q = 0.0;
+    PairAcc acc;
+    pair_reset(acc);
     int last_p = -1, key = -1, rslot = -1;
-    for (int x = 0; x < b; ++x) {
+    auto one = [&](int x, unsigned long long r0, unsigned long long r1, unsigned long long r2) {
         const int p = lrow[x];
         if (p != last_p) { last_p = p; key = quartet_pair_key(a, p, q, r, a.idepth[p], dq, dr, rslot); }
-        if (key < 0) continue;
-        const unsigned long long c0 = ((unsigned long long)tab[x * 3 + 0] * a.count_scale) & a.cint_mask;
-        const unsigned long long c1 = ((unsigned long long)tab[x * 3 + 1] * a.count_scale) & a.cint_mask;
-        const unsigned long long c2 = ((unsigned long long)tab[x * 3 + 2] * a.count_scale) & a.cint_mask;
-        pair_add(a, acc, key, rslot, c0, c1, c2, memo_t, memo_q);
+        if (key < 0) return;
+        pair_add(a, acc, key, rslot, (r0 * a.count_scale) & a.cint_mask, (r1 * a.count_scale) & a.cint_mask, (r2 * a.count_scale) & a.cint_mask);
+    };
+    int x = 0;
+    if (sizeof(CINT) == 2) {
+        // the run of b entries is contiguous: read it 8 entries (48 bytes = 3 x LDG.128) at a time once the entry index is a
+        // multiple of 8 — a thread's scalar 2-byte loads cost one L1 wavefront each, 24 per 8 entries instead of 3.  The 48
+        // bytes sit in 12 registers used as a shift register (6 bytes out per entry), so the loop body — with its fp64
+        // log_score and atomics — exists ONCE: unrolling it 8x made the kernel 11k instructions and 30x slower
+        // (instruction-cache misses under divergence, profiles/r01_k_*).
+        const uint64_t e0 = quartet_rank(0, b, c, d) - a.rank_base;
+        for (; x < b && ((e0 + x) & 7); ++x) one(x, tab[x * 3 + 0], tab[x * 3 + 1], tab[x * 3 + 2]);
+        for (; x + 8 <= b; x += 8) {
+            const uint4* v = reinterpret_cast<const uint4*>(tab + (size_t)x * 3);
+            const uint4 w0 = __ldg(v), w1 = __ldg(v + 1), w2 = __ldg(v + 2);
+            uint32_t w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#pragma unroll 1
+            for (int i = 0; i < 8; ++i) {
+                one(x + i, w[0] & 0xffffu, w[0] >> 16, w[1] & 0xffffu);
+#pragma unroll
+                for (int k = 0; k < 10; ++k) w[k] = __funnelshift_r(w[k + 1], w[k + 2], 16);      // >> 48 bits
+                w[10] = w[11] >> 16;
+            }
+        }
     }
+    for (; x < b; ++x) one(x, tab[x * 3 + 0], tab[x * 3 + 1], tab[x * 3 + 2]);
     pair_flush(a, acc);
 }
 

@@ -16,6 +16,8 @@
 #include <algorithm>
 #include <limits>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "kernels/common.cuh"
@@ -85,7 +87,7 @@ struct qs_ctx {
     size_t table_bytes = 0;
     RowTask* d_tasks = nullptr;  // task table of the d-range [plan_dB, plan_dE)
     size_t tasks_cap = 0;
-    int plan_dB = -1, plan_dE = -1, plan_nx = 0, plan_ny = 0, plan_max_rows = 1;
+    int plan_dB = -1, plan_dE = -1, plan_with_y = 0, plan_nx = 0, plan_ny = 0, plan_max_rows = 1;
     int64_t* d_enum = nullptr;   // PXO | PXD | PY | CD prefix tables of the plan
     bool counted = false;
     bool counted_once = false;   // n_class_a holds the class split of an earlier qs_count on this context
@@ -93,6 +95,7 @@ struct qs_ctx {
     // scoring
     unsigned long long* d_pair_sums = nullptr;
     unsigned long long* d_pair_best = nullptr;
+    int* d_pair_hint = nullptr;
     std::vector<unsigned long long> h_pair_sums, h_pair_best;
     bool fused_partials_valid = false;   // table-free mode: partials accumulated by qs_count
     int fused_scale = 1;
@@ -169,7 +172,7 @@ void free_all(qs_ctx* c) {
     cudaFree(c->d_D); cudaFree(c->d_flags); cudaFree(c->d_table);
     cudaFree(c->d_class); cudaFree(c->d_order); cudaFree(c->d_nA); cudaFree(c->d_counter);
     cudaFree(c->d_tasks); cudaFree(c->d_enum);
-    cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best);
+    cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best); cudaFree(c->d_pair_hint);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
 }
@@ -287,7 +290,7 @@ void task_row_intervals(const HostEnum& H, int kind, int64_t e0, int ne, int n, 
     iv.swap(m);
 }
 
-void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, std::vector<RowTask>& xt, std::vector<RowTask>& yt) {
+void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, std::vector<RowTask>& xt, std::vector<RowTask>& yt, bool with_y = true) {
     xt.clear(); yt.clear();
     std::vector<std::pair<int, int>> iv;
     auto rows_of = [&](const std::vector<std::pair<int, int>>& v) { int r = 0; for (auto& x : v) r += x.second - x.first + 1; return r; };
@@ -309,22 +312,35 @@ void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, std
     };
     emit(xt, ITEM_XO, H.PXO[n], CR_THREADS);
     emit(xt, ITEM_XD, H.PXD[n], 2 * CR_THREADS);
-    emit(yt, ITEM_Y, H.PY[n], 2 * CR_THREADS);
+    if (with_y) emit(yt, ITEM_Y, H.PY[n], 2 * CR_THREADS);
 }
 
-int ensure_plan(qs_ctx* c, int dB, int dE) {
-    if (c->plan_dB == dB && c->plan_dE == dE) return QS_OK;
-    const size_t row_bytes = (size_t)c->n_pad * 2;
-    // shared-memory budget per staged tree: ~24 KB (the whole matrix when n <= ~110), at least 4 rows
-    const int max_rows = (int)std::max<size_t>(4, std::min<size_t>((size_t)c->n, (24 * 1024) / row_bytes));
-    if ((size_t)max_rows * row_bytes * 2 + CR_SMEM_HEADER + 256 > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: matrix rows of %zu bytes are too long for the counting kernel's shared-memory pipeline", c->n, row_bytes);
+// host half of a plan: everything that needs no CUDA call, so that a helper thread can prepare the next slab's plan
+// while the GPU counts the current one (run_table_free)
+struct HostPlan {
+    int dB = -1, dE = -1, with_y = 0, max_rows = 1;
     HostEnum H;
-    build_enum_tables(c->n, dB, dE, H);
     std::vector<RowTask> xt, yt;
-    build_row_tasks(H, c->n, dB, dE, max_rows, xt, yt);
-    if (xt.size() + yt.size() > 0x3fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
+};
+
+void build_host_plan(int n, int n_pad, int dB, int dE, bool with_y, HostPlan& P) {
+    const size_t row_bytes = (size_t)n_pad * 2;
+    // shared-memory budget per staged tree: ~24 KB (the whole matrix when n <= ~110), at least 4 rows
+    const int max_rows = (int)std::max<size_t>(4, std::min<size_t>((size_t)n, (24 * 1024) / row_bytes));
+    P.dB = dB; P.dE = dE; P.with_y = with_y ? 1 : 0;
+    build_enum_tables(n, dB, dE, P.H);
+    build_row_tasks(P.H, n, dB, dE, max_rows, P.xt, P.yt, with_y);
     int mx = 1;
-    for (auto* v : {&xt, &yt}) for (auto& t : *v) mx = std::max(mx, t.rcount[0] + t.rcount[1] + t.rcount[2]);
+    for (auto* v : {&P.xt, &P.yt}) for (auto& t : *v) mx = std::max(mx, t.rcount[0] + t.rcount[1] + t.rcount[2]);
+    P.max_rows = mx;
+}
+
+// device half: upload a host plan (the stream is drained first: a running kernel may still read the previous tables)
+int upload_plan(qs_ctx* c, const HostPlan& P) {
+    const size_t row_bytes = (size_t)c->n_pad * 2;
+    if ((size_t)P.max_rows * row_bytes * 2 + CR_SMEM_HEADER + 256 > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: matrix rows of %zu bytes are too long for the counting kernel's shared-memory pipeline", c->n, row_bytes);
+    const std::vector<RowTask>&xt = P.xt, &yt = P.yt;
+    if (xt.size() + yt.size() > 0x3fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
     const size_t total = xt.size() + yt.size();
     int r;
     if (total > c->tasks_cap) {
@@ -332,16 +348,28 @@ int ensure_plan(qs_ctx* c, int dB, int dE) {
         c->tasks_cap = total + total / 4;
     }
     if (!c->d_enum && (r = dev_alloc(c, &c->d_enum, (size_t)4 * (c->n + 1)))) return r;
-    QS_CUDA(c, cudaStreamSynchronize(c->stream));      // a running kernel may still read the previous tables
+    QS_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!xt.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks, xt.data(), xt.size() * sizeof(RowTask), cudaMemcpyHostToDevice));
     if (!yt.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks + xt.size(), yt.data(), yt.size() * sizeof(RowTask), cudaMemcpyHostToDevice));
     const size_t np1 = (size_t)c->n + 1;
-    QS_CUDA(c, cudaMemcpy(c->d_enum, H.PXO.data(), np1 * 8, cudaMemcpyHostToDevice));
-    QS_CUDA(c, cudaMemcpy(c->d_enum + np1, H.PXD.data(), np1 * 8, cudaMemcpyHostToDevice));
-    QS_CUDA(c, cudaMemcpy(c->d_enum + 2 * np1, H.PY.data(), np1 * 8, cudaMemcpyHostToDevice));
-    QS_CUDA(c, cudaMemcpy(c->d_enum + 3 * np1, H.CD.data(), np1 * 8, cudaMemcpyHostToDevice));
-    c->plan_dB = dB; c->plan_dE = dE; c->plan_nx = (int)xt.size(); c->plan_ny = (int)yt.size(); c->plan_max_rows = mx;
+    QS_CUDA(c, cudaMemcpy(c->d_enum, P.H.PXO.data(), np1 * 8, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_enum + np1, P.H.PXD.data(), np1 * 8, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_enum + 2 * np1, P.H.PY.data(), np1 * 8, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_enum + 3 * np1, P.H.CD.data(), np1 * 8, cudaMemcpyHostToDevice));
+    c->plan_dB = P.dB; c->plan_dE = P.dE; c->plan_with_y = P.with_y; c->plan_nx = (int)xt.size(); c->plan_ny = (int)yt.size(); c->plan_max_rows = P.max_rows;
     return QS_OK;
+}
+
+// role-Y tasks are only needed (and only planned) when some gene tree is class B
+bool plan_needs_y(const qs_ctx* c) { return c->n_class_a < c->m; }
+
+int ensure_plan(qs_ctx* c, int dB, int dE, const HostPlan* ready = nullptr) {
+    const int with_y = plan_needs_y(c) ? 1 : 0;
+    if (c->plan_dB == dB && c->plan_dE == dE && c->plan_with_y >= with_y) return QS_OK;
+    if (ready && ready->dB == dB && ready->dE == dE && ready->with_y >= with_y) return upload_plan(c, *ready);
+    HostPlan P;
+    build_host_plan(c->n, c->n_pad, dB, dE, with_y != 0, P);
+    return upload_plan(c, P);
 }
 
 template <typename CINT>
@@ -361,12 +389,12 @@ void launch_finalize(qs_ctx* c, void* table, uint64_t n_entries) {
 }
 
 // count the quartets with d in [dB, dE) into `table` (rank_base = C(dB,4)); the distance matrices must be built
-int run_count_rows(qs_ctx* c, int dB, int dE, void* table) {
+int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready = nullptr) {
     const uint64_t rb = binom4((uint64_t)dB), re = binom4((uint64_t)dE);
     const uint64_t nq = re - rb;
     if (nq == 0) return QS_OK;
     int r;
-    if ((r = ensure_plan(c, dB, dE))) return r;
+    if ((r = ensure_plan(c, dB, dE, ready))) return r;
     switch (c->cint_bytes) {
         case 1: launch_init<uint8_t>(c, table, nq); break;
         case 2: launch_init<uint16_t>(c, table, nq); break;
@@ -390,7 +418,7 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table) {
     a.ring_bytes = (uint32_t)budget;
     // tree chunks: <= 4096 trees (fp16 counters) and >= 256; among the chunk counts that give the dynamic scheduler
     // 6..16 tasks per SM pick the one whose last round of tasks is fullest (tasks of one kind take the same time)
-    const bool all_a = !c->counted_once || c->n_class_a == c->m;
+    const bool all_a = c->n_class_a == c->m;
     const int64_t base = std::max<int64_t>(1, (int64_t)a.n_x + (all_a ? 0 : a.n_y));
     int64_t best_k = 1; double best_eff = -1;
     for (int64_t k = std::max<int64_t>(1, (c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES); k <= std::max<int64_t>(1, c->m / 256); ++k) {
@@ -532,6 +560,7 @@ int ensure_pair_arrays(qs_ctx* c) {
     int r;
     if (!c->d_pair_sums && (r = dev_alloc(c, &c->d_pair_sums, I * I * 3))) return r;
     if (!c->d_pair_best && (r = dev_alloc(c, &c->d_pair_best, I * I))) return r;
+    if (!c->d_pair_hint && (r = dev_alloc(c, &c->d_pair_hint, I * I))) return r;
     return QS_OK;
 }
 
@@ -539,6 +568,9 @@ int clear_pair_arrays(qs_ctx* c) {
     const size_t I = c->ref.n_inner;
     QS_CUDA(c, cudaMemsetAsync(c->d_pair_sums, 0, I * I * 3 * 8, c->stream));
     QS_CUDA(c, cudaMemsetAsync(c->d_pair_best, 0xFF, I * I * 8, c->stream));
+    qs_fill_int_kernel<<<(unsigned)std::min<size_t>((I * I + 255) / 256, 4096), 256, 0, c->stream>>>(c->d_pair_hint, I * I, QS_HINT_NONE);
+    c->launches++;
+    QS_CUDA(c, cudaGetLastError());
     return QS_OK;
 }
 
@@ -549,7 +581,7 @@ int scan_table(qs_ctx* c, const void* table, int dB, int dE, int count_scale) {
     if (c->score_blocks == 0) return QS_OK;
     ScoreArgs a;
     a.table = table; a.rank_base = binom4((uint64_t)dB); a.lca = c->d_lca; a.idepth = c->d_idepth;
-    a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.PB = c->d_PB; a.n = c->n; a.I = c->ref.n_inner;
+    a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.pair_hint = c->d_pair_hint; a.PB = c->d_PB; a.n = c->n; a.I = c->ref.n_inner;
     a.d_begin = dB; a.d_end = dE; a.count_scale = count_scale; a.cint_mask = cint_mask(c->cint_bytes);
     a.bifurcating = c->ref.bifurcating ? 1 : 0;
     switch (c->cint_bytes) {
@@ -574,23 +606,48 @@ int run_table_free(qs_ctx* c) {
     size_t budget = (free_b + c->table_bytes) / 10 * 6;                 // leave room for the distance matrices of a later, larger run
     if (const char* env = getenv("QS_SLAB_BYTES")) budget = (size_t)strtoull(env, nullptr, 10);   // test hook: force several slabs
     const size_t eb = 3 * (size_t)c->cint_bytes;
-    int dB = std::max(3, c->d_begin);
-    while (dB < c->d_end) {
-        // largest dE (8-aligned when possible, so that role Y's d-blocks are full) whose slab fits the budget
+    // slabs: largest dE (8-aligned when possible, so that role Y's d-blocks are full) whose table fits the budget
+    std::vector<std::pair<int, int>> slabs;
+    for (int dB = std::max(3, c->d_begin); dB < c->d_end;) {
         int dE = dB + 1;
         while (dE < c->d_end && (binom4((uint64_t)dE + 1) - binom4((uint64_t)dB)) * eb <= budget) ++dE;
         if (dE < c->d_end && dE - dB > 8) dE = std::max(dB + 1, dE & ~7);
+        slabs.emplace_back(dB, dE);
+        dB = dE;
+    }
+    // the host plan of slab k+1 (task table: up to ~1e6 tasks at n = 2000) is built by a helper thread while the GPU counts slab k
+    const bool with_y = plan_needs_y(c);
+    HostPlan plans[2];
+    std::thread planner;
+    auto start_plan = [&](size_t k) {
+        if (k >= slabs.size()) return;
+        HostPlan* P = &plans[k & 1];
+        const int n = c->n, n_pad = c->n_pad, b0 = slabs[k].first, e0 = slabs[k].second;
+        planner = std::thread([=]() { build_host_plan(n, n_pad, b0, e0, with_y, *P); });
+    };
+    start_plan(0);
+    int rc = QS_OK;
+    for (size_t k = 0; k < slabs.size() && rc == QS_OK; ++k) {
+        const int dB = slabs[k].first, dE = slabs[k].second;
+        planner.join();
+        start_plan(k + 1);
         const size_t need = (size_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB)) * eb;
         if (need > c->table_bytes) {
             if (c->d_table) { cudaFree(c->d_table); c->d_table = nullptr; c->table_bytes = 0; }
             cudaError_t e = cudaMalloc(&c->d_table, need);
-            if (e != cudaSuccess) { cudaGetLastError(); QS_FAIL(c, QS_E_MEMORY, "Insufficient memory! a slab of %zu bytes (d in [%d,%d)) does not fit this device", need, dB, dE); }
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                char b_[256];
+                snprintf(b_, sizeof b_, "Insufficient memory! a slab of %zu bytes (d in [%d,%d)) does not fit this device", need, dB, dE);
+                c->err = b_; rc = QS_E_MEMORY; break;
+            }
             c->table_bytes = need;
         }
-        if ((r = run_count_rows(c, dB, dE, c->d_table))) return r;
-        if ((r = scan_table(c, c->d_table, dB, dE, c->fused_scale))) return r;
-        dB = dE;
+        if ((rc = run_count_rows(c, dB, dE, c->d_table, &plans[k & 1]))) break;
+        rc = scan_table(c, c->d_table, dB, dE, c->fused_scale);
     }
+    if (planner.joinable()) planner.join();
+    if (rc) return rc;
     c->fused_partials_valid = true;
     return QS_OK;
 }
@@ -634,20 +691,52 @@ void for_path_edges(const HostRef& R, int u, int v, F f) {
     }
 }
 
+// The two host post-passes below visit every inner-node pair and walk its path (O(I^2 x depth): 5e5 pairs at
+// n = 1000).  Rows of the pair matrix are dealt round-robin to host threads; every thread keeps private per-edge
+// minima that are merged at the end, so the result does not depend on the thread count.
+template <typename F>
+void for_pair_rows_parallel(int I, int E, int n_arrays, double* const* out, F body) {
+    const double inf = std::numeric_limits<double>::infinity();
+    int nt = (I < 256) ? 1 : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* env = getenv("QS_HOST_THREADS")) nt = std::max(1, std::min(64, atoi(env)));      // explicit host thread count (tests; -t)
+    nt = std::max(1, std::min(nt, I));
+    std::vector<std::vector<double>> local((size_t)nt * n_arrays, std::vector<double>((size_t)E, inf));
+    auto work = [&](int w) {
+        double* mine[2] = {nullptr, nullptr};
+        for (int k = 0; k < n_arrays; ++k) mine[k] = local[(size_t)w * n_arrays + k].data();
+        for (int iu = w; iu < I; iu += nt) body(iu, mine);
+    };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (int w = 0; w < nt; ++w) th.emplace_back(work, w);
+        for (auto& t : th) t.join();
+    }
+    for (int k = 0; k < n_arrays; ++k) {
+        if (!out[k]) continue;
+        for (int e = 0; e < E; ++e) {
+            double m = inf;
+            for (int w = 0; w < nt; ++w) m = std::min(m, local[(size_t)w * n_arrays + k][e]);
+            out[k][e] = m;
+        }
+    }
+}
+
 // LQ-IC partial of this shard: exact (host libm) QIC of each pair's selected quartet, min over path edges
 void lqic_from_pairs(const qs_ctx* c, double* lqic) {
     const HostRef& R = c->ref;
     const int I = R.n_inner, E = R.n_nodes - 1;
-    const double inf = std::numeric_limits<double>::infinity();
-    for (int e = 0; e < E; ++e) lqic[e] = inf;
     const uint64_t M = (1ull << QS_TRIPLE_BITS) - 1;
-    for (int iu = 0; iu < I; ++iu)
+    double* out[1] = {lqic};
+    for_pair_rows_parallel(I, E, 1, out, [&](int iu, double* const* mine) {
+        double* lq = mine[0];
         for (int iv = iu + 1; iv < I; ++iv) {
             const unsigned long long t = c->h_pair_best[(size_t)iu * I + iv];
             if (t == QS_TRIPLE_NONE) continue;
             const double qic = host_log_score(t >> (2 * QS_TRIPLE_BITS), (t >> QS_TRIPLE_BITS) & M, t & M);
-            for_path_edges(R, R.inner_node[iu], R.inner_node[iv], [&](int e) { if (qic < lqic[e]) lqic[e] = qic; });
+            for_path_edges(R, R.inner_node[iu], R.inner_node[iv], [&](int e) { if (qic < lq[e]) lq[e] = qic; });
         }
+    });
 }
 
 // QP-IC / EQP-IC from (reduced) pair sums: QuartetScoreComputer.hpp:472-489
@@ -657,22 +746,24 @@ void qp_from_pairs(const qs_ctx* c, const uint64_t* sums, int exact_qp, double* 
     const double inf = std::numeric_limits<double>::infinity();
     for (int e = 0; e < E; ++e) { if (qpic) qpic[e] = inf; if (eqpic) eqpic[e] = inf; }
     if (!R.bifurcating) return;
-    for (int iu = 0; iu < I; ++iu)
+    double* out[2] = {qpic, eqpic};
+    for_pair_rows_parallel(I, E, 2, out, [&](int iu, double* const* mine) {
+        double *qpl = mine[0], *eql = mine[1];
         for (int iv = iu + 1; iv < I; ++iv) {
             const uint64_t* s = sums + ((size_t)iu * I + iv) * 3;
             uint64_t p1 = s[0], p2 = s[1], p3 = s[2];
             if (!exact_qp) { p1 &= 0xffffffffull; p2 &= 0xffffffffull; p3 &= 0xffffffffull; }   // `unsigned p1,p2,p3` (:382)
             const double qp = host_log_score(p1, p2, p3);
             const int u = R.inner_node[iu], v = R.inner_node[iv];
-            // :475-481 adjacency through the primary links (for the root: its first child link)
+            // :475-481 adjacency through the primary links (for the root: its first child link); an edge has one adjacent pair,
+            // so the private arrays hold at most one finite QP-IC per edge and the final min-merge is an assignment
             const int u_outer = (u == 0) ? R.first_child[0] : R.parent[u];
             const int v_outer = (v == 0) ? R.first_child[0] : R.parent[v];
-            if (qpic) {
-                if (u_outer == v) qpic[(u == 0) ? R.parent_edge[v] : R.parent_edge[u]] = qp;
-                else if (v_outer == u) qpic[(v == 0) ? R.parent_edge[u] : R.parent_edge[v]] = qp;
-            }
-            if (eqpic) for_path_edges(R, u, v, [&](int e) { if (qp < eqpic[e]) eqpic[e] = qp; });
+            if (u_outer == v) qpl[(u == 0) ? R.parent_edge[v] : R.parent_edge[u]] = qp;
+            else if (v_outer == u) qpl[(v == 0) ? R.parent_edge[u] : R.parent_edge[v]] = qp;
+            for_path_edges(R, u, v, [&](int e) { if (qp < eql[e]) eql[e] = qp; });
         }
+    });
 }
 
 }  // namespace
@@ -777,6 +868,7 @@ int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int3
     QS_CUDA(ctx, cudaMemcpy(ctx->d_idepth, ctx->ref.idepth.data(), (size_t)ctx->ref.n_inner * 2, cudaMemcpyHostToDevice));
     if (ctx->d_pair_sums) { cudaFree(ctx->d_pair_sums); ctx->d_pair_sums = nullptr; }
     if (ctx->d_pair_best) { cudaFree(ctx->d_pair_best); ctx->d_pair_best = nullptr; }
+    if (ctx->d_pair_hint) { cudaFree(ctx->d_pair_hint); ctx->d_pair_hint = nullptr; }
     ctx->score_dB = ctx->score_dE = -1;
     ctx->fused_partials_valid = false;
     ctx->has_ref = true;
@@ -860,6 +952,16 @@ int qs_count(qs_ctx* ctx) {
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     if ((r = run_distances(ctx))) return r;
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
+    // the class split decides the task table (no role-Y tasks are planned when every tree is class A) and a malformed
+    // tree should fail before the long kernel, so the host waits for the distance kernels here (they are < 1 % of a step)
+    int flags[2] = {0, 0};
+    int32_t nA = 0;
+    QS_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+    QS_CUDA(ctx, cudaMemcpyAsync(&nA, ctx->d_nA, sizeof(nA), cudaMemcpyDeviceToHost, ctx->stream));
+    QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->n_class_a = nA; ctx->counted_once = true;
+    if (flags[1] != 0) QS_FAIL(ctx, QS_E_TREE, "malformed evaluation tree (code %d): need parent[i] < i, leaf ids in [0,n) exactly on leaves, each taxon at most once per tree", flags[1]);
+    if (flags[0] > kMaxHalfExact) QS_FAIL(ctx, QS_E_UNSUPPORTED, "an evaluation tree has a leaf-to-leaf path of %d edges; this build packs distances in fp16 (exact up to %d)", flags[0], kMaxHalfExact);
     const uint64_t nq = ctx->rank_end - ctx->rank_begin;
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     if (ctx->mode == QS_MODE_TABLE) {
@@ -875,17 +977,10 @@ int qs_count(qs_ctx* ctx) {
         if ((r = run_table_free(ctx))) return r;
     }
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    int flags[2] = {0, 0};
-    int32_t nA = 0;
-    QS_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
-    QS_CUDA(ctx, cudaMemcpyAsync(&nA, ctx->d_nA, sizeof(nA), cudaMemcpyDeviceToHost, ctx->stream));
     QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->n_class_a = nA; ctx->counted_once = true;
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->dist_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->count_ms = ms;
-    if (flags[1] != 0) QS_FAIL(ctx, QS_E_TREE, "malformed evaluation tree (code %d): need parent[i] < i, leaf ids in [0,n) exactly on leaves, each taxon at most once per tree", flags[1]);
-    if (flags[0] > kMaxHalfExact) QS_FAIL(ctx, QS_E_UNSUPPORTED, "an evaluation tree has a leaf-to-leaf path of %d edges; this build packs distances in fp16 (exact up to %d)", flags[0], kMaxHalfExact);
     ctx->counted = true;
     return QS_OK;
 }

@@ -294,3 +294,21 @@ def test_table_save_load_roundtrip(tmp_path):
     with Context(ref.n_taxa, 1) as ctx:                    # wrong counter width is refused
         with pytest.raises(Exception):
             ctx.load_table(path)
+
+
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_scores_vs_oracle_wide_reference(threads, monkeypatch):
+    """120 taxa: rows long enough for the vectorised table scan, host post-pass forced onto several threads."""
+    monkeypatch.setenv("QS_HOST_THREADS", threads)
+    s = SyntheticInput(120, 300, 61, k_max=15, p_missing=0.05, p_contract=0.03, want_newick=False)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    with run_ctx(ref, s.flat) as ctx:
+        table = ctx.get_counts().astype(np.uint32)
+        got = {scale: ctx.score(scale) for scale in (1, 2)}
+    for scale in (1, 2):
+        wl, wq, we, bif = O.score(ref, table, scale, 16)
+        assert bif
+        for g, want in zip(got[scale], (wl, wq, we)):
+            assert np.array_equal(np.isinf(g), np.isinf(want))
+            fin = np.isfinite(want)
+            assert np.allclose(g[fin], want[fin], rtol=0, atol=1e-9)

@@ -165,3 +165,27 @@ def test_two_rank_gloo_exchange_reproduces_reference_scores(case, golden):
             assert np.array_equal(np.isinf(got), np.isinf(want)), key
             fin = np.isfinite(want)
             assert np.allclose(got[fin], want[fin], rtol=0, atol=1e-9), key
+
+
+def test_host_finalize_is_thread_count_independent(monkeypatch):
+    """qs_score_finalize on a 300-taxon reference (host-only context): the threaded pair post-pass must give the
+    single-thread result bit for bit."""
+    from quartetscores_b200.newick import flatten_reference, parse_newick
+    from quartetscores_b200.synth import SyntheticInput
+
+    s = SyntheticInput(300, 1, 77, k_max=0, want_newick=False)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    rng = np.random.default_rng(5)
+    out = {}
+    for th in ("1", "7"):
+        monkeypatch.setenv("QS_HOST_THREADS", th)
+        with Context(ref.n_taxa, 2, device=QS_DEVICE_NONE) as ctx:
+            ctx.set_reference(ref)
+            P = ctx.num_pairs()
+            if "sums" not in out:
+                out["sums"] = rng.integers(0, 1 << 34, size=P * 3, dtype=np.uint64)
+                out["lq"] = rng.standard_normal(ref.edge_count)
+            out[th] = ctx.score_finalize(out["lq"], out["sums"])
+    for a, b in zip(out["1"], out["7"]):
+        assert np.array_equal(a, b)
+    assert np.isfinite(out["1"][2]).sum() > 250          # EQP-IC reaches every internal edge
