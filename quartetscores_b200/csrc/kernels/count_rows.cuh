@@ -78,11 +78,12 @@ struct CountRowsArgs {
     int d_begin, d_end;         // shard: quartets with d in [d_begin, d_end)
     uint32_t row_bytes;         // n_pad * 2
     uint32_t ring_bytes;        // shared memory available to the staging ring (every task sizes its own stages from it)
+    int max_tps, max_stages;    // caps of the ring geometry (<= 32 trees per stage: one lane issues the copies of one tree; <= CR_MAX_STAGES)
 };
 
 constexpr int CR_THREADS = 512;
 constexpr int CR_MAX_STAGES = 8;
-constexpr int CR_MAX_TPS = 8;
+constexpr int CR_MAX_TPS = 32;        // one lane issues the copies of one tree
 constexpr int CR_SMEM_HEADER = 128 + 4 * 4096;     // barriers + done counters + the chunk's tree ids (QS_MAX_CHUNK_TREES)
 
 // ---- the enumerations (shared by the host task builder and the kernel) ---------------------------------------
@@ -180,13 +181,14 @@ __device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, 
     const int ntrees = t1 - t0;
     const size_t tree_elems = (size_t)a.n * a.n_pad;
     // pipeline geometry of THIS task: a staged tree takes only the rows the task touches (a few KB for most tasks, the
-    // whole matrix only for the few tasks with tiny c), so the ring is as deep as the shared-memory budget allows:
-    // up to CR_MAX_TPS trees per stage x CR_MAX_STAGES stages.  A shallow ring (sized for the worst task) left the
-    // warps waiting on the refill latency for 14 % of their time (profiles/r01_f_*).
+    // whole matrix only for the few tasks with tiny c), so a stage holds up to CR_MAX_TPS trees.  Stages sized for the
+    // worst task (3 trees each, round 1e) cost 12 % at cfg2 (profiles/r01_f_*, r01_g_*).
     const uint32_t slot = (uint32_t)(T.rcount[0] + T.rcount[1] + T.rcount[2]) * a.row_bytes;            // bytes staged per tree
-    int tps = CR_MAX_TPS;
-    while (tps > 1 && (uint32_t)(3 * tps) * slot > a.ring_bytes) --tps;
-    const int n_stages = min(CR_MAX_STAGES, (int)(a.ring_bytes / ((uint32_t)tps * slot)));
+    // the hand-over between stages (mbarrier wait, shared-memory atomic, refill) costs ~600 clk per stage and the ring
+    // depth does not matter beyond 2 (profiles/r01_p_sweep_*): as many trees per stage as two stages allow
+    int tps = a.max_tps;
+    while (tps > 1 && (uint32_t)(2 * tps) * slot > a.ring_bytes) --tps;
+    const int n_stages = min(a.max_stages, (int)(a.ring_bytes / ((uint32_t)tps * slot)));
     const uint32_t stage_bytes = (uint32_t)tps * slot;
     const int nst = (ntrees + tps - 1) / tps;
     // lanes 0..tps-1 of the calling warp copy the rows of the trees of stage st

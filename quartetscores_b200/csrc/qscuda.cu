@@ -416,8 +416,11 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
     const size_t max_slot = (size_t)c->plan_max_rows * a.row_bytes;
     if (2 * max_slot > budget) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: two pipeline stages of %zu-byte row slots do not fit in shared memory", c->n, max_slot);
     a.ring_bytes = (uint32_t)budget;
+    a.max_tps = CR_MAX_TPS; a.max_stages = CR_MAX_STAGES;
+    if (const char* env = getenv("QS_MAX_TPS")) a.max_tps = std::max(1, std::min(32, atoi(env)));             // tuning hooks
+    if (const char* env = getenv("QS_MAX_STAGES")) a.max_stages = std::max(2, std::min((int)CR_MAX_STAGES, atoi(env)));
     // tree chunks: <= 4096 trees (fp16 counters) and >= 256; among the chunk counts that give the dynamic scheduler
-    // 6..16 tasks per SM pick the one whose last round of tasks is fullest (tasks of one kind take the same time)
+    // 3..16 tasks per SM pick the smallest one whose last round of tasks is (nearly) the fullest
     const bool all_a = c->n_class_a == c->m;
     const int64_t base = std::max<int64_t>(1, (int64_t)a.n_x + (all_a ? 0 : a.n_y));
     int64_t best_k = 1; double best_eff = -1;
@@ -425,8 +428,12 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
         const int64_t T = base * k, rounds = (T + c->num_sms - 1) / c->num_sms;
         if (rounds > 16 && best_eff >= 0) break;
         double eff = (double)T / (double)(rounds * c->num_sms);
-        if (rounds < 6) eff *= 0.5 + rounds / 12.0;                 // too few tasks per SM: uneven task lengths dominate
-        if (eff > best_eff + 1e-9) { best_eff = eff; best_k = k; }
+        if (rounds < 3) eff *= 0.7 + rounds * 0.1;                  // too few tasks per SM: uneven task lengths dominate
+        if (eff > best_eff + 0.005) { best_eff = eff; best_k = k; } // fewer chunks (fewer flushes) unless clearly fuller (r01_p_sweep_*)
+    }
+    if (const char* env = getenv("QS_CHUNK_COUNT")) {                  // tuning hook: force the number of tree chunks
+        const int64_t k = atoll(env);
+        if (k >= 1) best_k = std::max<int64_t>(k, (c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES);
     }
     a.chunk_trees = (int)std::min<int64_t>(QS_MAX_CHUNK_TREES, std::max<int64_t>(1, (c->m + best_k - 1) / best_k));
     const size_t smem = CR_SMEM_HEADER + budget;
