@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libqscuda.so")
+LIB_PATH = os.environ.get("QSCUDA_LIB") or os.path.join(_HERE, "libqscuda.so")   # QSCUDA_LIB: tuning builds (tools/)
 
 QS_OK = 0
 QS_MODE_TABLE = 0

@@ -81,7 +81,19 @@ struct CountRowsArgs {
     int max_tps, max_stages;    // caps of the ring geometry (<= 32 trees per stage: one lane issues the copies of one tree; <= CR_MAX_STAGES)
 };
 
-constexpr int CR_THREADS = 512;
+#ifndef CR_UNROLL_PF
+#define CR_UNROLL_PF 2          // trees per iteration of the tree loop: 2 is 2.2 % faster than 1 at cfg2 (profiles/r01_r_*)
+#endif
+#ifndef CR_UNROLL_HALVES
+#define CR_UNROLL_HALVES 1
+#endif
+constexpr int kUnrollPf = CR_UNROLL_PF, kUnrollHalves = CR_UNROLL_HALVES;
+// CTA shapes of the counting kernel (template parameters THREADS, CTAS per SM), always 16 warps per SM:
+//   512 x 1 : one CTA owns the SM's whole staging ring — best while a task's rows are a large part of the matrix (n <= 112)
+//   256 x 2 : two independent CTAs per SM desynchronise the stage hand-overs — 5-9 % faster from n = 128 up
+// (profiles/r01_u_variants.txt).  A task holds THREADS thread-items, so the host plan is built for the shape in use.
+constexpr int CR_THREADS_BIG = 512, CR_THREADS_SMALL = 256;
+__host__ __device__ constexpr int cr_ctas_per_sm(int threads) { return CR_THREADS_BIG / threads; }
 constexpr int CR_MAX_STAGES = 8;
 constexpr int CR_MAX_TPS = 32;        // one lane issues the copies of one tree
 constexpr int CR_SMEM_HEADER = 128 + 4 * 4096;     // barriers + done counters + the chunk's tree ids (QS_MAX_CHUNK_TREES)
@@ -154,7 +166,7 @@ struct RowPipe {
 template <class LD, class MT>
 __device__ __forceinline__ void stage_pf(const unsigned char* base, int nt, uint32_t slot, LD&& ld, MT&& mt) {
     auto cur = ld(base);
-#pragma unroll 1
+#pragma unroll kUnrollPf
     for (int tt = 0; tt < nt; ++tt) {
         if (tt + 1 < nt) base += slot;               // (the last tree of a stage re-reads itself: no branch around the loads)
         auto nx = ld(base);
@@ -165,7 +177,7 @@ __device__ __forceinline__ void stage_pf(const unsigned char* base, int nt, uint
 template <class LDA, class LDB, class MTA, class MTB>
 __device__ __forceinline__ void stage_halves(const unsigned char* base, int nt, uint32_t slot, LDA&& lda, LDB&& ldb, MTA&& mta, MTB&& mtb) {
     auto ca = lda(base);
-#pragma unroll 1
+#pragma unroll kUnrollHalves
     for (int tt = 0; tt < nt; ++tt) {
         auto cb = ldb(base);
         mta(ca);
@@ -175,7 +187,7 @@ __device__ __forceinline__ void stage_halves(const unsigned char* base, int nt, 
     }
 }
 
-template <class STAGE>
+template <int THREADS, class STAGE>
 __device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, const RowTask& T, int t0, int t1, STAGE&& stage) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int ntrees = t1 - t0;
@@ -207,7 +219,7 @@ __device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, 
         }
     };
     __syncthreads();                 // the previous task's readers are done with every stage and with P.trees
-    for (int i = tid; i < ntrees; i += CR_THREADS) P.trees[i] = a.order[t0 + i];
+    for (int i = tid; i < ntrees; i += THREADS) P.trees[i] = a.order[t0 + i];
     if (tid < CR_MAX_STAGES) P.done[tid] = 0;
     __syncthreads();
     if (tid < 32)
@@ -220,7 +232,7 @@ __device__ __forceinline__ void stream_rows(const CountRowsArgs& a, RowPipe& P, 
         stage(P.bufs + (size_t)buf * stage_bytes, nt, slot);
         __syncwarp();
         int last = 0;
-        if (lane == 0) last = (atomicAdd(&P.done[buf], 1) == CR_THREADS / 32 - 1);
+        if (lane == 0) last = (atomicAdd(&P.done[buf], 1) == THREADS / 32 - 1);
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {                                  // last warp out refills the stage
             if (lane == 0) P.done[buf] = 0;
@@ -241,7 +253,8 @@ __device__ __forceinline__ uint32_t cr_row_off(const RowTask& T, int row, uint32
     return (uint32_t)slot * row_bytes;
 }
 
-__global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const CountRowsArgs a) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, cr_ctas_per_sm(THREADS)) qs_count_rows_kernel(const CountRowsArgs a) {
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ int s_task;
     RowPipe P;
@@ -295,7 +308,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
             const uint32_t rp = valid ? cr_row_off(T, c, rb) : 0u, rq = valid ? cr_row_off(T, d, rb) : 0u;
             const uint32_t oPu = rp + ia * 16u, oQu = rq + ia * 16u, oPv = rp + ib * 16u, oQv = rq + ib * 16u;
             XCounters x; zero(x);
-            stream_rows(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
+            stream_rows<THREADS>(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
                 stage_pf(base, nt, slot,
                          [&](const unsigned char* s) { return BlockRows{lds128(s, oPu), lds128(s, oQu), lds128(s, oPv), lds128(s, oQv)}; },
                          [&](const BlockRows& r) { step_gt_lt(x, r); });
@@ -329,7 +342,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
             const uint32_t oAp = (vA ? cr_row_off(T, cA, rb) : 0u) + jA * 16u, oAq = (vA ? cr_row_off(T, dA, rb) : 0u) + jA * 16u;
             const uint32_t oBp = (vB ? cr_row_off(T, cB, rb) : 0u) + jB * 16u, oBq = (vB ? cr_row_off(T, dB, rb) : 0u) + jB * 16u;
             GCounters ga, gb; zero(ga); zero(gb);
-            stream_rows(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
+            stream_rows<THREADS>(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
                 stage_pf(base, nt, slot,
                          [&](const unsigned char* s) { return BlockRows{lds128(s, oAp), lds128(s, oAq), lds128(s, oBp), lds128(s, oBq)}; },
                          [&](const BlockRows& r) { step_gt_diag(ga, r.pu, r.qu); step_gt_diag(gb, r.pv, r.qv); });
@@ -368,7 +381,7 @@ __global__ void __launch_bounds__(CR_THREADS, 1) qs_count_rows_kernel(const Coun
             const uint32_t oApu = pA + iaA * 16u, oAqu = qA + iaA * 16u, oApv = pA + idA * 16u, oAqv = qA + idA * 16u;
             const uint32_t oBpu = pB + iaB * 16u, oBqu = qB + iaB * 16u, oBpv = pB + idB * 16u, oBqv = qB + idB * 16u;
             GCounters ga, gb; zero(ga); zero(gb);
-            stream_rows(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
+            stream_rows<THREADS>(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
                 stage_halves(base, nt, slot,
                              [&](const unsigned char* s) { return BlockRows{lds128(s, oApu), lds128(s, oAqu), lds128(s, oApv), lds128(s, oAqv)}; },
                              [&](const unsigned char* s) { return BlockRows{lds128(s, oBpu), lds128(s, oBqu), lds128(s, oBpv), lds128(s, oBqv)}; },

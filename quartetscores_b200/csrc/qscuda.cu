@@ -87,7 +87,7 @@ struct qs_ctx {
     size_t table_bytes = 0;
     RowTask* d_tasks = nullptr;  // task table of the d-range [plan_dB, plan_dE)
     size_t tasks_cap = 0;
-    int plan_dB = -1, plan_dE = -1, plan_with_y = 0, plan_nx = 0, plan_ny = 0, plan_max_rows = 1;
+    int plan_dB = -1, plan_dE = -1, plan_with_y = 0, plan_threads = 0, plan_nx = 0, plan_ny = 0, plan_max_rows = 1;
     int64_t* d_enum = nullptr;   // PXO | PXD | PY | CD prefix tables of the plan
     bool counted = false;
     bool counted_once = false;   // n_class_a holds the class split of an earlier qs_count on this context
@@ -290,7 +290,7 @@ void task_row_intervals(const HostEnum& H, int kind, int64_t e0, int ne, int n, 
     iv.swap(m);
 }
 
-void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, std::vector<RowTask>& xt, std::vector<RowTask>& yt, bool with_y = true) {
+void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, int threads, std::vector<RowTask>& xt, std::vector<RowTask>& yt, bool with_y = true) {
     xt.clear(); yt.clear();
     std::vector<std::pair<int, int>> iv;
     auto rows_of = [&](const std::vector<std::pair<int, int>>& v) { int r = 0; for (auto& x : v) r += x.second - x.first + 1; return r; };
@@ -310,26 +310,32 @@ void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, std
             e += ne;
         }
     };
-    emit(xt, ITEM_XO, H.PXO[n], CR_THREADS);
-    emit(xt, ITEM_XD, H.PXD[n], 2 * CR_THREADS);
-    if (with_y) emit(yt, ITEM_Y, H.PY[n], 2 * CR_THREADS);
+    emit(xt, ITEM_XO, H.PXO[n], threads);
+    emit(xt, ITEM_XD, H.PXD[n], 2 * threads);
+    if (with_y) emit(yt, ITEM_Y, H.PY[n], 2 * threads);
 }
 
 // host half of a plan: everything that needs no CUDA call, so that a helper thread can prepare the next slab's plan
 // while the GPU counts the current one (run_table_free)
+// CTA shape of the counting kernel for n taxa (kernels/count_rows.cuh); QS_CR_THREADS = 512 | 256 overrides (tuning)
+int cr_threads_for(int n) {
+    if (const char* env = getenv("QS_CR_THREADS")) { const int t = atoi(env); if (t == CR_THREADS_BIG || t == CR_THREADS_SMALL) return t; }
+    return n <= 112 ? CR_THREADS_BIG : CR_THREADS_SMALL;        // measured crossover between n = 100 and n = 128 (profiles/r01_v_shape_threshold.txt)
+}
+
 struct HostPlan {
-    int dB = -1, dE = -1, with_y = 0, max_rows = 1;
+    int dB = -1, dE = -1, with_y = 0, max_rows = 1, threads = CR_THREADS_BIG;
     HostEnum H;
     std::vector<RowTask> xt, yt;
 };
 
-void build_host_plan(int n, int n_pad, int dB, int dE, bool with_y, HostPlan& P) {
+void build_host_plan(int n, int n_pad, int dB, int dE, bool with_y, int threads, HostPlan& P) {
     const size_t row_bytes = (size_t)n_pad * 2;
     // shared-memory budget per staged tree: ~24 KB (the whole matrix when n <= ~110), at least 4 rows
     const int max_rows = (int)std::max<size_t>(4, std::min<size_t>((size_t)n, (24 * 1024) / row_bytes));
-    P.dB = dB; P.dE = dE; P.with_y = with_y ? 1 : 0;
+    P.dB = dB; P.dE = dE; P.with_y = with_y ? 1 : 0; P.threads = threads;
     build_enum_tables(n, dB, dE, P.H);
-    build_row_tasks(P.H, n, dB, dE, max_rows, P.xt, P.yt, with_y);
+    build_row_tasks(P.H, n, dB, dE, max_rows, threads, P.xt, P.yt, with_y);
     int mx = 1;
     for (auto* v : {&P.xt, &P.yt}) for (auto& t : *v) mx = std::max(mx, t.rcount[0] + t.rcount[1] + t.rcount[2]);
     P.max_rows = mx;
@@ -338,7 +344,7 @@ void build_host_plan(int n, int n_pad, int dB, int dE, bool with_y, HostPlan& P)
 // device half: upload a host plan (the stream is drained first: a running kernel may still read the previous tables)
 int upload_plan(qs_ctx* c, const HostPlan& P) {
     const size_t row_bytes = (size_t)c->n_pad * 2;
-    if ((size_t)P.max_rows * row_bytes * 2 + CR_SMEM_HEADER + 256 > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: matrix rows of %zu bytes are too long for the counting kernel's shared-memory pipeline", c->n, row_bytes);
+    if ((size_t)P.max_rows * row_bytes * 2 + CR_SMEM_HEADER + 256 + 1024 > (size_t)c->smem_optin / cr_ctas_per_sm(P.threads)) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: matrix rows of %zu bytes are too long for the counting kernel's shared-memory pipeline", c->n, row_bytes);
     const std::vector<RowTask>&xt = P.xt, &yt = P.yt;
     if (xt.size() + yt.size() > 0x3fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
     const size_t total = xt.size() + yt.size();
@@ -356,7 +362,7 @@ int upload_plan(qs_ctx* c, const HostPlan& P) {
     QS_CUDA(c, cudaMemcpy(c->d_enum + np1, P.H.PXD.data(), np1 * 8, cudaMemcpyHostToDevice));
     QS_CUDA(c, cudaMemcpy(c->d_enum + 2 * np1, P.H.PY.data(), np1 * 8, cudaMemcpyHostToDevice));
     QS_CUDA(c, cudaMemcpy(c->d_enum + 3 * np1, P.H.CD.data(), np1 * 8, cudaMemcpyHostToDevice));
-    c->plan_dB = P.dB; c->plan_dE = P.dE; c->plan_with_y = P.with_y; c->plan_nx = (int)xt.size(); c->plan_ny = (int)yt.size(); c->plan_max_rows = P.max_rows;
+    c->plan_dB = P.dB; c->plan_dE = P.dE; c->plan_with_y = P.with_y; c->plan_threads = P.threads; c->plan_nx = (int)xt.size(); c->plan_ny = (int)yt.size(); c->plan_max_rows = P.max_rows;
     return QS_OK;
 }
 
@@ -364,11 +370,11 @@ int upload_plan(qs_ctx* c, const HostPlan& P) {
 bool plan_needs_y(const qs_ctx* c) { return c->n_class_a < c->m; }
 
 int ensure_plan(qs_ctx* c, int dB, int dE, const HostPlan* ready = nullptr) {
-    const int with_y = plan_needs_y(c) ? 1 : 0;
-    if (c->plan_dB == dB && c->plan_dE == dE && c->plan_with_y >= with_y) return QS_OK;
-    if (ready && ready->dB == dB && ready->dE == dE && ready->with_y >= with_y) return upload_plan(c, *ready);
+    const int with_y = plan_needs_y(c) ? 1 : 0, threads = cr_threads_for(c->n);
+    if (c->plan_dB == dB && c->plan_dE == dE && c->plan_with_y >= with_y && c->plan_threads == threads) return QS_OK;
+    if (ready && ready->dB == dB && ready->dE == dE && ready->with_y >= with_y && ready->threads == threads) return upload_plan(c, *ready);
     HostPlan P;
-    build_host_plan(c->n, c->n_pad, dB, dE, with_y != 0, P);
+    build_host_plan(c->n, c->n_pad, dB, dE, with_y != 0, threads, P);
     return upload_plan(c, P);
 }
 
@@ -412,7 +418,8 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
     a.row_bytes = (uint32_t)c->n_pad * 2u;
     // staging ring: all the shared memory the CTA can get; every task sizes its own stages from the rows it touches
     // (kernels/count_rows.cuh: stream_rows), the largest task must fit twice
-    const size_t budget = ((size_t)c->smem_optin - CR_SMEM_HEADER - 256) & ~(size_t)127;
+    const int threads = c->plan_threads, ctas = cr_ctas_per_sm(threads);
+    const size_t budget = ((size_t)c->smem_optin / ctas - CR_SMEM_HEADER - 256 - (ctas > 1 ? 1024 : 0)) & ~(size_t)127;
     const size_t max_slot = (size_t)c->plan_max_rows * a.row_bytes;
     if (2 * max_slot > budget) QS_FAIL(c, QS_E_UNSUPPORTED, "%d taxa: two pipeline stages of %zu-byte row slots do not fit in shared memory", c->n, max_slot);
     a.ring_bytes = (uint32_t)budget;
@@ -425,9 +432,10 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
     const int64_t base = std::max<int64_t>(1, (int64_t)a.n_x + (all_a ? 0 : a.n_y));
     int64_t best_k = 1; double best_eff = -1;
     for (int64_t k = std::max<int64_t>(1, (c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES); k <= std::max<int64_t>(1, c->m / 256); ++k) {
-        const int64_t T = base * k, rounds = (T + c->num_sms - 1) / c->num_sms;
+        const int64_t slots = (int64_t)c->num_sms * ctas;
+        const int64_t T = base * k, rounds = (T + slots - 1) / slots;
         if (rounds > 16 && best_eff >= 0) break;
-        double eff = (double)T / (double)(rounds * c->num_sms);
+        double eff = (double)T / (double)(rounds * slots);
         if (rounds < 3) eff *= 0.7 + rounds * 0.1;                  // too few tasks per SM: uneven task lengths dominate
         if (eff > best_eff + 0.005) { best_eff = eff; best_k = k; } // fewer chunks (fewer flushes) unless clearly fuller (r01_p_sweep_*)
     }
@@ -437,11 +445,13 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
     }
     a.chunk_trees = (int)std::min<int64_t>(QS_MAX_CHUNK_TREES, std::max<int64_t>(1, (c->m + best_k - 1) / best_k));
     const size_t smem = CR_SMEM_HEADER + budget;
-    QS_CUDA(c, cudaFuncSetAttribute(qs_count_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (threads == CR_THREADS_BIG) QS_CUDA(c, cudaFuncSetAttribute(qs_count_rows_kernel<CR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else QS_CUDA(c, cudaFuncSetAttribute(qs_count_rows_kernel<CR_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t max_tasks = ((int64_t)a.n_x + a.n_y) * 2 * ((c->m + a.chunk_trees - 1) / a.chunk_trees + 1);
     if (max_tasks > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "task count overflow");
-    const int grid = (int)std::min<int64_t>(max_tasks, c->num_sms);
-    qs_count_rows_kernel<<<grid, CR_THREADS, smem, c->stream>>>(a);
+    const int grid = (int)std::min<int64_t>(max_tasks, (int64_t)c->num_sms * ctas);
+    if (threads == CR_THREADS_BIG) qs_count_rows_kernel<CR_THREADS_BIG><<<grid, CR_THREADS_BIG, smem, c->stream>>>(a);
+    else qs_count_rows_kernel<CR_THREADS_SMALL><<<grid, CR_THREADS_SMALL, smem, c->stream>>>(a);
     c->launches++;
     QS_CUDA(c, cudaGetLastError());
     switch (c->cint_bytes) {
@@ -630,7 +640,8 @@ int run_table_free(qs_ctx* c) {
         if (k >= slabs.size()) return;
         HostPlan* P = &plans[k & 1];
         const int n = c->n, n_pad = c->n_pad, b0 = slabs[k].first, e0 = slabs[k].second;
-        planner = std::thread([=]() { build_host_plan(n, n_pad, b0, e0, with_y, *P); });
+        const int threads = cr_threads_for(n);
+        planner = std::thread([=]() { build_host_plan(n, n_pad, b0, e0, with_y, threads, *P); });
     };
     start_plan(0);
     int rc = QS_OK;
@@ -1049,9 +1060,10 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
     HostEnum H;
     build_enum_tables(n_taxa, dB, dE, H);
     std::vector<RowTask> xt, yt;
-    build_row_tasks(H, n_taxa, dB, dE, max_rows, xt, yt);
+    const int threads = cr_threads_for(n_taxa);
+    build_row_tasks(H, n_taxa, dB, dE, max_rows, threads, xt, yt);
     int64_t items[3] = {0, 0, 0}, slots[3] = {0, 0, 0}, rows = 0, mx = 0, violations = 0, quartets = 0;
-    const int cap[3] = {CR_THREADS, 2 * CR_THREADS, 2 * CR_THREADS};
+    const int cap[3] = {threads, 2 * threads, 2 * threads};
     int64_t next_e[3] = {0, 0, 0};
     auto in_ranges = [](const RowTask& t, int row) {
         for (int k = 0; k < 3; ++k) if (row >= t.rstart[k] && row < t.rstart[k] + t.rcount[k]) return true;

@@ -312,3 +312,24 @@ def test_scores_vs_oracle_wide_reference(threads, monkeypatch):
             assert np.array_equal(np.isinf(g), np.isinf(want))
             fin = np.isfinite(want)
             assert np.allclose(g[fin], want[fin], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("threads", ["512", "256"])
+@pytest.mark.parametrize("name", ["s32x270_spr", "s16x300_missing_poly", "s24x60_u8"])
+def test_golden_counts_both_cta_shapes(name, threads, golden, monkeypatch):
+    """the counting kernel has two CTA shapes (512 x 1 for n < 150, 256 x 2 above): both must give the reference's table"""
+    monkeypatch.setenv("QS_CR_THREADS", threads)
+    g = golden(name)
+    _, ref, flat = load_input(g)
+    with run_ctx(ref, flat) as ctx:
+        assert np.array_equal(ctx.get_counts().astype(np.uint32), g["counts"].astype(np.uint32))
+
+
+def test_counts_vs_oracle_small_cta_shape_default():
+    """160 taxa selects the 256 x 2 shape by itself (n > 112); class-B trees so that role Y runs too.  Few trees: the oracle is O(n^4 m)."""
+    s = SyntheticInput(160, 4, 71, k_max=25, p_missing=0.08, p_contract=0.05, want_newick=False)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    want = O.count_clades_compact(160, s.flat) // 2
+    with run_ctx(ref, s.flat) as ctx:
+        got = ctx.get_counts().astype(np.uint32)
+    assert np.array_equal(got, want)
