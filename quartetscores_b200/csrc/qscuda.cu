@@ -15,6 +15,9 @@
 
 #include <algorithm>
 #include <limits>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <utility>
@@ -712,24 +715,66 @@ void for_path_edges(const HostRef& R, int u, int v, F f) {
 // The two host post-passes below visit every inner-node pair and walk its path (O(I^2 x depth): 5e5 pairs at
 // n = 1000).  Rows of the pair matrix are dealt round-robin to host threads; every thread keeps private per-edge
 // minima that are merged at the end, so the result does not depend on the thread count.
+// A process-wide pool of parked host threads for these passes: at n = 100 a pass is only ~0.3 ms of work, so threads are
+// woken (condition variable, ~10 us) rather than created per call.  Leaked on purpose: the workers are detached and
+// must not be joined from a static destructor at library unload.
+class HostPool {
+public:
+    static HostPool& get() { static HostPool* p = new HostPool(); return *p; }
+    // run job(w) for w in [0, nt): w = 0 on the calling thread, the rest on pool workers; returns when all are done
+    void run(int nt, const std::function<void(int)>& job) {
+        if (nt <= 1) { job(0); return; }
+        std::unique_lock<std::mutex> run_lock(run_mu_);          // one parallel region at a time (contexts may share the pool)
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            while ((int)workers_ < nt - 1) { std::thread(&HostPool::worker, this, (int)workers_ + 1).detach(); ++workers_; }
+            job_ = &job; n_active_ = nt; pending_ = nt - 1; ++generation_;
+        }
+        cv_.notify_all();
+        job(0);
+        std::unique_lock<std::mutex> g(mu_);
+        done_cv_.wait(g, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+private:
+    void worker(int id) {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* job = nullptr;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return generation_ != seen; });
+                seen = generation_;
+                if (id < n_active_) job = job_;
+            }
+            if (job) {
+                (*job)(id);
+                std::lock_guard<std::mutex> g(mu_);
+                if (--pending_ == 0) done_cv_.notify_one();
+            }
+        }
+    }
+    std::mutex mu_, run_mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* job_ = nullptr;
+    uint64_t generation_ = 0;
+    int n_active_ = 0, pending_ = 0;
+    size_t workers_ = 0;
+};
+
 template <typename F>
 void for_pair_rows_parallel(int I, int E, int n_arrays, double* const* out, F body) {
     const double inf = std::numeric_limits<double>::infinity();
-    int nt = (I < 256) ? 1 : (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    const int hw = (int)std::max(1u, std::thread::hardware_concurrency());
+    int nt = (I < 48) ? 1 : std::min(I < 256 ? 8 : 16, hw);
     if (const char* env = getenv("QS_HOST_THREADS")) nt = std::max(1, std::min(64, atoi(env)));      // explicit host thread count (tests; -t)
     nt = std::max(1, std::min(nt, I));
     std::vector<std::vector<double>> local((size_t)nt * n_arrays, std::vector<double>((size_t)E, inf));
-    auto work = [&](int w) {
+    HostPool::get().run(nt, [&](int w) {
         double* mine[2] = {nullptr, nullptr};
         for (int k = 0; k < n_arrays; ++k) mine[k] = local[(size_t)w * n_arrays + k].data();
         for (int iu = w; iu < I; iu += nt) body(iu, mine);
-    };
-    if (nt == 1) work(0);
-    else {
-        std::vector<std::thread> th;
-        for (int w = 0; w < nt; ++w) th.emplace_back(work, w);
-        for (auto& t : th) t.join();
-    }
+    });
     for (int k = 0; k < n_arrays; ++k) {
         if (!out[k]) continue;
         for (int e = 0; e < E; ++e) {
