@@ -20,31 +20,59 @@
 namespace qs {
 
 constexpr int QS_MAX_CHUNK_TREES = 4096;
-constexpr float QS_COUNTER_BIAS = 2048.f;
 
-struct XCounters { __half2 gt[8][4], lt[8][4]; };   // 8 (v) x 8 (u, packed in pairs): G(u)>G(v), G(u)<G(v)
-struct GCounters { __half2 gt[8][4]; };             // 8 x 8, G(u)>G(v) only
+#ifndef QS_INT_COUNTERS
+#define QS_INT_COUNTERS 0
+#endif
+
+#if QS_INT_COUNTERS
+// Tuning build: integer-mask compare (HSET2 -> 0xFFFF per true half) and a TWO-input integer subtract per compare, which
+// ptxas places on the FMA pipe as IMAD.IADD: 1.71 compares+accumulates/clk/SM in isolation against 1.55 for
+// HSET2.BF + HADD2 (tools/ubench_mix2.cu, profiles/r01_w_ubench_mix2.txt).  Subtracting 0xFFFF from a 16-bit half adds 1
+// to it and borrows 1 from the upper half, so after L low-half and H high-half hits acc = L + 65536 (H - L) mod 2^32.
+typedef uint32_t ctr_t;
+__device__ __forceinline__ ctr_t ctr_zero() { return 0u; }
+#if QS_INT_COUNTERS == 2      // keep every subtract a separate two-input instruction (ptxas otherwise fuses two trees into one IADD3)
+__device__ __forceinline__ void acc_sub(ctr_t& acc, uint32_t m) { asm volatile("sub.s32 %0, %0, %1;" : "+r"(acc) : "r"(m)); }
+#else
+__device__ __forceinline__ void acc_sub(ctr_t& acc, uint32_t m) { acc -= m; }
+#endif
+__device__ __forceinline__ void acc_gt(ctr_t& acc, __half2 u, __half2 b) { acc_sub(acc, __hgt2_mask(u, b)); }
+__device__ __forceinline__ void acc_lt(ctr_t& acc, __half2 u, __half2 b) { acc_sub(acc, __hlt2_mask(u, b)); }
+__device__ __forceinline__ void decode(ctr_t acc, uint32_t& lo, uint32_t& hi) {
+    lo = acc & 0xffffu;
+    hi = ((acc >> 16) + lo) & 0xffffu;
+}
+#else
+constexpr float QS_COUNTER_BIAS = 2048.f;
+typedef __half2 ctr_t;
+__device__ __forceinline__ ctr_t ctr_zero() { return __float2half2_rn(-QS_COUNTER_BIAS); }
+__device__ __forceinline__ void acc_gt(ctr_t& acc, __half2 u, __half2 b) { acc = __hadd2(acc, __hgt2(u, b)); }
+__device__ __forceinline__ void acc_lt(ctr_t& acc, __half2 u, __half2 b) { acc = __hadd2(acc, __hlt2(u, b)); }
+// packed counter -> (hits of the low half, hits of the high half)
+__device__ __forceinline__ void decode(ctr_t acc, uint32_t& lo, uint32_t& hi) {
+    const float2 f = __half22float2(acc);
+    lo = (uint32_t)(f.x + QS_COUNTER_BIAS);
+    hi = (uint32_t)(f.y + QS_COUNTER_BIAS);
+}
+#endif
+
+struct XCounters { ctr_t gt[8][4], lt[8][4]; };   // 8 (v) x 8 (u, packed in pairs): G(u)>G(v), G(u)<G(v)
+struct GCounters { ctr_t gt[8][4]; };             // 8 x 8, G(u)>G(v) only
 
 __device__ __forceinline__ void zero(XCounters& x) {
-    const __half2 z = __float2half2_rn(-QS_COUNTER_BIAS);
+    const ctr_t z = ctr_zero();
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int p = 0; p < 4; ++p) { x.gt[j][p] = z; x.lt[j][p] = z; }
 }
 __device__ __forceinline__ void zero(GCounters& y) {
-    const __half2 z = __float2half2_rn(-QS_COUNTER_BIAS);
+    const ctr_t z = ctr_zero();
 #pragma unroll
     for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int p = 0; p < 4; ++p) y.gt[j][p] = z;
-}
-
-// packed counter -> (hits of the low half, hits of the high half)
-__device__ __forceinline__ void decode(__half2 acc, uint32_t& lo, uint32_t& hi) {
-    const float2 f = __half22float2(acc);
-    lo = (uint32_t)(f.x + QS_COUNTER_BIAS);
-    hi = (uint32_t)(f.y + QS_COUNTER_BIAS);
 }
 
 __device__ __forceinline__ void sub4(__half2 (&g)[4], const uint4& hi, const uint4& lo) {
@@ -65,8 +93,8 @@ __device__ __forceinline__ void step_gt_lt(XCounters& x, const BlockRows& r) {
         const __half2 b = (j & 1) ? __high2half2(v[j >> 1]) : __low2half2(v[j >> 1]);
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
-            x.gt[j][p] = __hadd2(x.gt[j][p], __hgt2(u[p], b));
-            x.lt[j][p] = __hadd2(x.lt[j][p], __hlt2(u[p], b));
+            acc_gt(x.gt[j][p], u[p], b);
+            acc_lt(x.lt[j][p], u[p], b);
         }
     }
 }
@@ -80,7 +108,7 @@ __device__ __forceinline__ void step_gt(GCounters& y, const BlockRows& r) {
     for (int j = 0; j < 8; ++j) {
         const __half2 b = (j & 1) ? __high2half2(v[j >> 1]) : __low2half2(v[j >> 1]);
 #pragma unroll
-        for (int p = 0; p < 4; ++p) y.gt[j][p] = __hadd2(y.gt[j][p], __hgt2(u[p], b));
+        for (int p = 0; p < 4; ++p) acc_gt(y.gt[j][p], u[p], b);
     }
 }
 
@@ -92,7 +120,7 @@ __device__ __forceinline__ void step_gt_diag(GCounters& y, const uint4& p, const
     for (int j = 0; j < 8; ++j) {
         const __half2 b = (j & 1) ? __high2half2(u[j >> 1]) : __low2half2(u[j >> 1]);
 #pragma unroll
-        for (int pp = 0; pp < 4; ++pp) y.gt[j][pp] = __hadd2(y.gt[j][pp], __hgt2(u[pp], b));
+        for (int pp = 0; pp < 4; ++pp) acc_gt(y.gt[j][pp], u[pp], b);
     }
 }
 
