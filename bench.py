@@ -53,9 +53,9 @@ TABLE_BYTES_LIMIT = 120e9      # a shard's uint16 table above this is not kept r
 HSET2_LANEOPS_PER_EVAL = {"A": 1.0, "B": 1.5}
 INT32_LANEOPS_PER_EVAL = 9.0       # 3 adds + 3 compares + 3 predicated increments
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the counting kernel from the committed `ncu --set full`
-# capture of the same workload on one GPU (profiles/r01_g_count_rows_cfg2_ncu_full.txt: 384.9 MB + 88.6 MB); null where
+# capture of the same workload on one GPU (profiles/r01_y_count_rows_cfg2_ncu_full.txt: 395.9 MB + 53.1 MB); null where
 # no capture of that exact workload exists
-NCU_DRAM_TRAFFIC_BYTES = {("cfg2", 1): 384936960 + 88566272}
+NCU_DRAM_TRAFFIC_BYTES = {("cfg2", 1): 395905280 + 53114368}
 
 
 def hbm_peak_gbs():
