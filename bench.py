@@ -136,6 +136,16 @@ def run_reference_binary(ref_nwk, eval_lines, threads, tmp, tag):
     return elapsed * 1e-6, took[0] * 1e-6, took[1] * 1e-6, kind
 
 
+def reference_full_estimate(nq, m, sample, elapsed, count_s, score_s):
+    """Evaluations/s of the reference on the WHOLE workload, from a run on the first `sample` trees: counting and Newick
+    parsing grow linearly with the tree count, the scoring pass over the C(n,4) quartets does not (it is the same for any
+    m), so quoting the sample's own throughput would understate the reference."""
+    r = m / float(sample)
+    other = max(0.0, elapsed - count_s - score_s)
+    full_s = count_s * r + score_s + other * r
+    return nq * m / full_s, full_s
+
+
 def reference_sample_size(w, target_evals):
     nq = comb(w["n_taxa"], 4)
     s = int(target_evals / nq)
@@ -150,22 +160,27 @@ def reference_arm(args, w, wname):
     sample = reference_sample_size(w, 2.0e9)
     inp = make_input(dict(w, n_trees=sample), want_newick=True)
     nq = comb(w["n_taxa"], 4)
-    times = []
+    times, parts = [], []
     kind = "?"
     with tempfile.TemporaryDirectory() as tmp:
         for i in range(args.warmup + args.steps):
             el, cnt, sc, kind = run_reference_binary(inp.ref_newick, inp.eval_newick, cores, tmp, "r")
             if i >= args.warmup:
                 times.append(el)
+                parts.append((cnt, sc))
     total = sum(times)
-    value = nq * sample * len(times) / total
+    sample_value = nq * sample * len(times) / total
+    mean = lambda xs: sum(xs) / len(xs)
+    value, full_s = reference_full_estimate(nq, w["n_trees"], sample, mean(times), mean([p[0] for p in parts]), mean([p[1] for p in parts]))
     line = {
         "impl": "reference", "metric": "quartet_tree_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic",
-        "config": {"workload": f"{wname}: {w['label']}", "sample": f"first {sample} of {w['n_trees']} gene trees per step (cost is linear in the tree count)"},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference",
-                         "sample": f"oracle/_ref/QuartetScores -t {cores}, {kind} table, {sample} trees x {nq} quartets per step, end-to-end 'Elapsed time' incl. Newick parsing"},
+        "config": {"workload": f"{wname}: {w['label']}", "sample": f"first {sample} of {w['n_trees']} gene trees per step"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference", "sample_value": sample_value,
+                         "sample": f"oracle/_ref/QuartetScores -t {cores}, {kind} table, first {sample} of {w['n_trees']} trees per step: {mean(times):.2f} s end-to-end "
+                                   f"({mean([p[0] for p in parts]):.2f} s counting, {mean([p[1] for p in parts]):.2f} s scoring); value = whole-workload estimate "
+                                   f"({full_s:.1f} s: counting and parsing scaled by the tree count, scoring constant); the sample's own throughput is sample_value"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -358,8 +373,11 @@ def main():
             sub = make_input(dict(w, n_trees=sample), want_newick=True)
             with tempfile.TemporaryDirectory() as tmp:
                 el, cnt, sc, kind = run_reference_binary(sub.ref_newick, sub.eval_newick, cores, tmp, "cpu")
-            line["cpu_baseline"] = {"value": nq * sample / el, "unit": "evals/s", "cores": cores, "kind": "reference",
-                                    "sample": f"oracle/_ref/QuartetScores -t {cores}, {kind} table, first {sample} of {m} trees: {el:.2f} s end-to-end ({cnt:.2f} s counting, {sc:.2f} s scoring)"}
+            full_value, full_s = reference_full_estimate(nq, m, sample, el, cnt, sc)
+            line["cpu_baseline"] = {"value": full_value, "unit": "evals/s", "cores": cores, "kind": "reference", "sample_value": nq * sample / el,
+                                    "sample": f"oracle/_ref/QuartetScores -t {cores}, {kind} table, first {sample} of {m} trees: {el:.2f} s end-to-end ({cnt:.2f} s counting, "
+                                              f"{sc:.2f} s scoring); value = whole-workload estimate ({full_s:.1f} s: counting and parsing scaled by the tree count, scoring "
+                                              f"constant); the sample's own throughput is sample_value"}
         except Exception as e:  # the oracle port is the documented fallback
             line["cpu_baseline"] = {"value": None, "unit": "evals/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {e}"}
     if rank == 0:
