@@ -194,8 +194,11 @@ __global__ void qs_fill_int_kernel(int* __restrict__ p, size_t n, int v) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+#ifndef QS_SCORE_MIN_BLOCKS
+#define QS_SCORE_MIN_BLOCKS 4      // CTAs of 128 threads per SM the compiler must leave room for (register cap = 65536 / (128 x this))
+#endif
 template <typename CINT>
-__global__ void __launch_bounds__(128) qs_score_table_kernel(const ScoreArgs a) {
+__global__ void __launch_bounds__(128, QS_SCORE_MIN_BLOCKS) qs_score_table_kernel(const ScoreArgs a) {
     // block -> b (uniform), thread -> (c,d) pair
     const long long blk = blockIdx.x;
     int lo = 1, hi = a.n - 2;              // b in [1, n-3]

@@ -1313,27 +1313,45 @@ int qs_write_raw_qic(qs_ctx* ctx, int count_scale, const char* const* taxon_name
         memcpy(&v, tab.data() + idx * eb, eb);
         return (v * (uint64_t)count_scale) & mask;
     };
-    // printRawQICScores order: a outermost .. d innermost (QuartetScoreComputer.hpp:626-629)
-    for (int a = 0; a < n; ++a) for (int b = a + 1; b < n; ++b) for (int cc = b + 1; cc < n; ++cc) {
-        const int p = R.lca[(size_t)a * n + b], q = R.lca[(size_t)b * n + cc];
-        const int dp = R.idepth[p], dq = R.idepth[q];
-        for (int d = cc + 1; d < n; ++d) {
-            const int dr = R.idepth[R.lca[(size_t)cc * n + d]];
-            const int S0 = dp + dr, S2 = std::min(dp, std::min(dq, dr)) + dq;
-            if (S0 == S2) continue;                                   // unresolved in the reference tree (:559-562)
-            const uint64_t rk = (quartet_rank(a, b, cc, d) - ctx->rank_begin) * 3;
-            const uint64_t c0 = get(rk), c1 = get(rk + 1), c2 = get(rk + 2);
-            char num[64];
-            if (S0 > S2) {
-                snprintf(num, sizeof(num), "%g", host_log_score(c0, c1, c2));
-                fprintf(f, "(%s,%s|%s,%s): %s\n", taxon_names[a], taxon_names[b], taxon_names[cc], taxon_names[d], num);
-            } else {
-                snprintf(num, sizeof(num), "%g", host_log_score(c2, c0, c1));    // (u,z|v,w): ab|cd=uz|vw, ac|bd=uv|zw, ad|bc=uw|zv
-                fprintf(f, "(%s,%s|%s,%s): %s\n", taxon_names[a], taxon_names[d], taxon_names[b], taxon_names[cc], num);
+    // printRawQICScores order: a outermost .. d innermost (QuartetScoreComputer.hpp:626-629).  The reference formats
+    // serially; here the lines of `nt` consecutive values of a are formatted by host threads into private buffers and
+    // written in order, so the file is byte-identical for any thread count.
+    auto format_a = [&](int a, std::string& out) {
+        char line[1200];
+        for (int b = a + 1; b < n; ++b) for (int cc = b + 1; cc < n; ++cc) {
+            const int p = R.lca[(size_t)a * n + b], q = R.lca[(size_t)b * n + cc];
+            const int dp = R.idepth[p], dq = R.idepth[q];
+            for (int d = cc + 1; d < n; ++d) {
+                const int dr = R.idepth[R.lca[(size_t)cc * n + d]];
+                const int S0 = dp + dr, S2 = std::min(dp, std::min(dq, dr)) + dq;
+                if (S0 == S2) continue;                                   // unresolved in the reference tree (:559-562)
+                const uint64_t rk = (quartet_rank(a, b, cc, d) - ctx->rank_begin) * 3;
+                const uint64_t c0 = get(rk), c1 = get(rk + 1), c2 = get(rk + 2);
+                int len;
+                if (S0 > S2) len = snprintf(line, sizeof line, "(%s,%s|%s,%s): %g\n", taxon_names[a], taxon_names[b], taxon_names[cc], taxon_names[d], host_log_score(c0, c1, c2));
+                else len = snprintf(line, sizeof line, "(%s,%s|%s,%s): %g\n", taxon_names[a], taxon_names[d], taxon_names[b], taxon_names[cc],
+                                    host_log_score(c2, c0, c1));              // (u,z|v,w): ab|cd=uz|vw, ac|bd=uv|zw, ad|bc=uw|zv
+                if (len >= (int)sizeof line) {                            // very long taxon labels: format again into a large enough buffer
+                    std::string big((size_t)len + 1, '\0');
+                    if (S0 > S2) snprintf(&big[0], big.size(), "(%s,%s|%s,%s): %g\n", taxon_names[a], taxon_names[b], taxon_names[cc], taxon_names[d], host_log_score(c0, c1, c2));
+                    else snprintf(&big[0], big.size(), "(%s,%s|%s,%s): %g\n", taxon_names[a], taxon_names[d], taxon_names[b], taxon_names[cc], host_log_score(c2, c0, c1));
+                    out.append(big.data(), (size_t)len);
+                } else out.append(line, (size_t)len);
             }
         }
+    };
+    int nt = (int)std::min<unsigned>(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char* env = getenv("QS_HOST_THREADS")) nt = std::max(1, std::min(64, atoi(env)));
+    if (n < 24) nt = 1;
+    std::vector<std::string> bufs((size_t)nt);
+    bool ok = true;
+    for (int a0 = 0; a0 < n && ok; a0 += nt) {
+        const int cnt = std::min(nt, n - a0);
+        HostPool::get().run(cnt, [&](int w) { bufs[(size_t)w].clear(); format_a(a0 + w, bufs[(size_t)w]); });
+        for (int w = 0; w < cnt && ok; ++w) ok = bufs[(size_t)w].empty() || fwrite(bufs[(size_t)w].data(), 1, bufs[(size_t)w].size(), f) == bufs[(size_t)w].size();
     }
-    fclose(f);
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) QS_FAIL(ctx, QS_E_ARG, "short write to %s", path);
     return QS_OK;
 }
 

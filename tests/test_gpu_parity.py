@@ -333,3 +333,34 @@ def test_counts_vs_oracle_small_cta_shape_default():
     with run_ctx(ref, s.flat) as ctx:
         got = ctx.get_counts().astype(np.uint32)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("cint_bytes", [4, 8])
+def test_wide_counter_types(cint_bytes, golden):
+    """uint32 / uint64 CINT (src/QuartetScores.cpp:115-147 picks them for m >= 65,536 / 2^32 trees): same counts, same scores."""
+    g = golden("s16x300_missing_poly")
+    _, ref, flat = load_input(g)
+    with Context(ref.n_taxa, cint_bytes) as ctx:
+        ctx.set_reference(ref)
+        ctx.add_trees(flat)
+        ctx.count()
+        got = ctx.get_counts()
+        assert got.dtype.itemsize == cint_bytes
+        assert np.array_equal(got.astype(np.uint64), g["counts"].astype(np.uint64))
+        lq, qp, eqp = ctx.score(1)
+    for a, key in ((lq, "lqic"), (qp, "qpic"), (eqp, "eqpic")):
+        want = g[key]
+        assert np.array_equal(np.isinf(a), np.isinf(want))
+        fin = np.isfinite(want)
+        assert np.allclose(a[fin], want[fin], rtol=0, atol=1e-9)
+
+
+@pytest.mark.parametrize("threads", ["1", "6"])
+def test_raw_qic_file_thread_count_independent(threads, golden, tmp_path, monkeypatch):
+    monkeypatch.setenv("QS_HOST_THREADS", threads)
+    g = golden("s32x270_spr")
+    _, ref, flat = load_input(g)
+    with run_ctx(ref, flat) as ctx:
+        p = str(tmp_path / "raw.txt")
+        ctx.write_raw_qic(ref.taxa, p)
+        assert open(p).read() == g["rawqic"]
