@@ -9,6 +9,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -720,7 +721,16 @@ void for_path_edges(const HostRef& R, int u, int v, F f) {
 // must not be joined from a static destructor at library unload.
 class HostPool {
 public:
-    static HostPool& get() { static HostPool* p = new HostPool(); return *p; }
+    static HostPool*& instance() { static HostPool* p = nullptr; return p; }
+    static HostPool& get() {
+        HostPool*& p = instance();
+        if (!p) {
+            p = new HostPool();
+            // a fork()ed child has none of the parent's threads: start over with an empty pool there
+            pthread_atfork(nullptr, nullptr, [] { instance() = new HostPool(); });
+        }
+        return *p;
+    }
     // run job(w) for w in [0, nt): w = 0 on the calling thread, the rest on pool workers; returns when all are done
     void run(int nt, const std::function<void(int)>& job) {
         if (nt <= 1) { job(0); return; }
