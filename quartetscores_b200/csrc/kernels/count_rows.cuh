@@ -29,7 +29,7 @@
 //       x<y gives slot 1 of (x,y), x>y gives slot 2 of (y,x) — half the cost of a full block   2 items / thread
 //   Y   (b; c; d-block; a-block): G(a)>G(d)                                                    2 items / thread
 // so a thread always carries 64 packed counter registers and issues 64 HSET2 + 64 HADD2 per tree.  A task
-// is a run of up to 512 thread-items of one kind; consecutive items share matrix rows, and the host records
+// is a run of up to THREADS (512 or 256, see below) thread-items of one kind; consecutive items share matrix rows, and the host records
 // the rows a task touches as at most three contiguous row ranges.  Only those rows are staged per tree
 // (n = 100: ~3 KB instead of the 21 KB matrix; n = 1000: 4 KB for 32,768 quartets = 0.12 B per evaluation).
 // Tasks x tree classes x tree chunks are handed to persistent CTAs through an atomic counter.  Counters are

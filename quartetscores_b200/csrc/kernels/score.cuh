@@ -195,7 +195,7 @@ __global__ void qs_fill_int_kernel(int* __restrict__ p, size_t n, int v) {
 }
 
 #ifndef QS_SCORE_MIN_BLOCKS
-#define QS_SCORE_MIN_BLOCKS 4      // CTAs of 128 threads per SM the compiler must leave room for (register cap = 65536 / (128 x this))
+#define QS_SCORE_MIN_BLOCKS 6      // CTAs of 128 threads per SM the compiler must leave room for (80 registers; 4 -> 104 regs is 6 % slower, 8 spills: profiles/r02_a_score_variants.txt)
 #endif
 template <typename CINT>
 __global__ void __launch_bounds__(128, QS_SCORE_MIN_BLOCKS) qs_score_table_kernel(const ScoreArgs a) {
