@@ -102,13 +102,14 @@ struct PairAcc {
     double best_q;                 // its exact score
     unsigned long long cand0, cand1, last_t;
     float bound;                   // smallest estimate / champion score seen in this run
+    int hint_bits;                 // pair_hint[key], requested when the run starts so that it has arrived by the time the run ends
     int ncand;
     int key;                       // pair index or -1
 };
 
 __device__ __forceinline__ void pair_reset(PairAcc& acc) {
     acc.s1 = acc.s2 = acc.s3 = 0; acc.best = QS_TRIPLE_NONE; acc.best_q = INFINITY; acc.key = -1;
-    acc.cand0 = acc.cand1 = acc.last_t = QS_TRIPLE_NONE; acc.bound = INFINITY; acc.ncand = 0;
+    acc.cand0 = acc.cand1 = acc.last_t = QS_TRIPLE_NONE; acc.bound = INFINITY; acc.ncand = 0; acc.hint_bits = QS_HINT_NONE;
 }
 
 // evaluate the pending candidates exactly and fold them into the champion
@@ -134,7 +135,7 @@ __device__ __forceinline__ void pair_flush(const ScoreArgs& a, PairAcc& acc) {
     // pair_hint never lies below the pair's true current minimum (it is lowered only AFTER a successful update of
     // pair_best, to a value rounded up), so a run whose every quartet is estimated above it cannot improve the pair:
     // no fp64 evaluation, no CAS.  Most runs end here.
-    const float hint = ordered_to_float(*reinterpret_cast<volatile int*>(a.pair_hint + acc.key));
+    const float hint = ordered_to_float(acc.hint_bits);      // read at the start of the run: stale only towards +inf, i.e. conservative
     if (acc.bound <= hint + QS_FILTER_MARGIN) {
         pair_resolve(acc);
         if (acc.best != QS_TRIPLE_NONE) {
@@ -156,7 +157,11 @@ __device__ __forceinline__ void pair_flush(const ScoreArgs& a, PairAcc& acc) {
 // one quartet's contribution; (c0,c1,c2) = table slots after scale/mask
 __device__ __forceinline__ void pair_add(const ScoreArgs& a, PairAcc& acc, int key, int rslot,
                                          unsigned long long c0, unsigned long long c1, unsigned long long c2) {
-    if (key != acc.key) { pair_flush(a, acc); acc.key = key; }
+    if (key != acc.key) {
+        pair_flush(a, acc);
+        acc.key = key;
+        acc.hint_bits = *reinterpret_cast<volatile int*>(a.pair_hint + key);      // in flight while the run is scanned (the flush stalled ~600 clk on it)
+    }
     unsigned long long q1, q2, q3;
     if (rslot == 0) { q1 = c0; q2 = c1; q3 = c2; }
     else if (a.bifurcating) { q1 = c2; q2 = c1; q3 = c0; }      // processNodePair order: (ref, S1S3|S2S4, S1S4|S2S3)
@@ -194,6 +199,9 @@ __global__ void qs_fill_int_kernel(int* __restrict__ p, size_t n, int v) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
+#ifndef QS_SCORE_PREFETCH
+#define QS_SCORE_PREFETCH 0
+#endif
 #ifndef QS_SCORE_MIN_BLOCKS
 #define QS_SCORE_MIN_BLOCKS 6      // CTAs of 128 threads per SM the compiler must leave room for (80 registers; 4 -> 104 regs is 6 % slower, 8 spills: profiles/r02_a_score_variants.txt)
 #endif
@@ -204,6 +212,15 @@ __global__ void __launch_bounds__(128, QS_SCORE_MIN_BLOCKS) qs_score_table_kerne
     int lo = 1, hi = a.n - 2;              // b in [1, n-3]
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (a.PB[mid] <= blk) lo = mid; else hi = mid; }
     const int b = lo;
+    // lca(a,b) and its depth for every a < b are the same for the whole block: staged once in shared memory as
+    // (inner index | depth << 16).  Read per quartet from global they were a chain of dependent L1 loads and, with the table
+    // reads, half of all warp stalls (profiles/r02_e_*).
+    extern __shared__ uint32_t s_pd[];
+    {
+        const uint16_t* lrow_g = a.lca + (size_t)b * a.n;
+        for (int x = threadIdx.x; x < b; x += blockDim.x) { const uint32_t p = lrow_g[x]; s_pd[x] = p | ((uint32_t)a.idepth[p] << 16); }
+    }
+    __syncthreads();
     const long long j = (blk - a.PB[b]) * blockDim.x + threadIdx.x;   // pair index for this b
     // pairs (c,d): d in [max(b+2,d_begin), d_end), c in (b, d); enumerate d-major
     // count of pairs with d' < d : sum_{d'=dlo}^{d-1} (d'-b-1)
@@ -223,14 +240,14 @@ __global__ void __launch_bounds__(128, QS_SCORE_MIN_BLOCKS) qs_score_table_kerne
     const int q = a.lca[(size_t)b * a.n + c], r = a.lca[(size_t)c * a.n + d];
     const int dq = a.idepth[q], dr = a.idepth[r];
     const CINT* tab = reinterpret_cast<const CINT*>(a.table) + (quartet_rank(0, b, c, d) - a.rank_base) * 3;
-    const uint16_t* lrow = a.lca + (size_t)b * a.n;
 
     PairAcc acc;
     pair_reset(acc);
     int last_p = -1, key = -1, rslot = -1;
     auto one = [&](int x, unsigned long long r0, unsigned long long r1, unsigned long long r2) {
-        const int p = lrow[x];
-        if (p != last_p) { last_p = p; key = quartet_pair_key(a, p, q, r, a.idepth[p], dq, dr, rslot); }
+        const uint32_t pd = s_pd[x];
+        const int p = (int)(pd & 0xffffu);
+        if (p != last_p) { last_p = p; key = quartet_pair_key(a, p, q, r, (int)(pd >> 16), dq, dr, rslot); }
         if (key < 0) return;
         pair_add(a, acc, key, rslot, (r0 * a.count_scale) & a.cint_mask, (r1 * a.count_scale) & a.cint_mask, (r2 * a.count_scale) & a.cint_mask);
     };
@@ -243,10 +260,20 @@ __global__ void __launch_bounds__(128, QS_SCORE_MIN_BLOCKS) qs_score_table_kerne
         // (instruction-cache misses under divergence, profiles/r01_k_*).
         const uint64_t e0 = quartet_rank(0, b, c, d) - a.rank_base;
         for (; x < b && ((e0 + x) & 7); ++x) one(x, tab[x * 3 + 0], tab[x * 3 + 1], tab[x * 3 + 2]);
+#if QS_SCORE_PREFETCH
+        // the next 48 bytes are requested before the current 8 entries are processed: the scan is latency-bound
+        // (issue-active 51 %, long-scoreboard stalls on these loads: profiles/r01_n_score_table_n500_ncu_full.txt)
+        uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, n2 = n0;
+        if (x + 8 <= b) { const uint4* v = reinterpret_cast<const uint4*>(tab + (size_t)x * 3); n0 = __ldg(v); n1 = __ldg(v + 1); n2 = __ldg(v + 2); }
+        for (; x + 8 <= b; x += 8) {
+            uint32_t w[12] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w};
+            if (x + 16 <= b) { const uint4* v = reinterpret_cast<const uint4*>(tab + (size_t)(x + 8) * 3); n0 = __ldg(v); n1 = __ldg(v + 1); n2 = __ldg(v + 2); }
+#else
         for (; x + 8 <= b; x += 8) {
             const uint4* v = reinterpret_cast<const uint4*>(tab + (size_t)x * 3);
             const uint4 w0 = __ldg(v), w1 = __ldg(v + 1), w2 = __ldg(v + 2);
             uint32_t w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+#endif
 #pragma unroll 1
             for (int i = 0; i < 8; ++i) {
                 one(x + i, w[0] & 0xffffu, w[0] >> 16, w[1] & 0xffffu);

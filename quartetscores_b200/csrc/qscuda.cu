@@ -183,7 +183,7 @@ void free_all(qs_ctx* c) {
 
 template <typename CINT>
 void launch_score(qs_ctx* c, const ScoreArgs& a) {
-    qs_score_table_kernel<CINT><<<(unsigned)c->score_blocks, 128, 0, c->stream>>>(a);
+    qs_score_table_kernel<CINT><<<(unsigned)c->score_blocks, 128, (size_t)c->n * sizeof(uint32_t), c->stream>>>(a);
     c->launches++;
 }
 
