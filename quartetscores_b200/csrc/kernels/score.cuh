@@ -21,6 +21,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef QS_SCORE_L2_PREFETCH
+#define QS_SCORE_L2_PREFETCH 1      // table reads carry the L2::256B prefetch hint (see ldg_l2_256)
+#endif
+
 namespace qs {
 
 struct ScoreArgs {
@@ -94,6 +98,19 @@ __device__ __forceinline__ float dev_log_score_f32(unsigned q1, unsigned q2, uns
     if (q3) { const float p = (float)q3 * inv; acc += p * __log2f(p); }
     const float qic = 1.f + acc * il3;
     return ((q1 < q2) || (q1 < q3)) ? -qic : qic;
+}
+
+// 16-byte read-only load that asks L2 to fetch the whole 256-byte neighbourhood from DRAM: a thread walks its run 48 bytes
+// at a time, so the next five visits then hit in L2 instead of opening the DRAM page again (the scan is bound by DRAM row
+// locality)
+__device__ __forceinline__ uint4 ldg_l2_256(const uint4* p) {
+    uint4 v;
+#if QS_SCORE_L2_PREFETCH
+    asm volatile("ld.global.nc.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+#else
+    v = __ldg(p);
+#endif
+    return v;
 }
 
 struct PairAcc {
@@ -264,14 +281,14 @@ __global__ void __launch_bounds__(128, QS_SCORE_MIN_BLOCKS) qs_score_table_kerne
         // the next 48 bytes are requested before the current 8 entries are processed: the scan is latency-bound
         // (issue-active 51 %, long-scoreboard stalls on these loads: profiles/r01_n_score_table_n500_ncu_full.txt)
         uint4 n0 = make_uint4(0, 0, 0, 0), n1 = n0, n2 = n0;
-        if (x + 8 <= b) { const uint4* v = reinterpret_cast<const uint4*>(tab + (size_t)x * 3); n0 = __ldg(v); n1 = __ldg(v + 1); n2 = __ldg(v + 2); }
+        if (x + 8 <= b) { const uint4* v = reinterpret_cast<const uint4*>(tab + (size_t)x * 3); n0 = ldg_l2_256(v); n1 = ldg_l2_256(v + 1); n2 = ldg_l2_256(v + 2); }
         for (; x + 8 <= b; x += 8) {
             uint32_t w[12] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w, n2.x, n2.y, n2.z, n2.w};
-            if (x + 16 <= b) { const uint4* v = reinterpret_cast<const uint4*>(tab + (size_t)(x + 8) * 3); n0 = __ldg(v); n1 = __ldg(v + 1); n2 = __ldg(v + 2); }
+            if (x + 16 <= b) { const uint4* v = reinterpret_cast<const uint4*>(tab + (size_t)(x + 8) * 3); n0 = ldg_l2_256(v); n1 = ldg_l2_256(v + 1); n2 = ldg_l2_256(v + 2); }
 #else
         for (; x + 8 <= b; x += 8) {
             const uint4* v = reinterpret_cast<const uint4*>(tab + (size_t)x * 3);
-            const uint4 w0 = __ldg(v), w1 = __ldg(v + 1), w2 = __ldg(v + 2);
+            const uint4 w0 = ldg_l2_256(v), w1 = ldg_l2_256(v + 1), w2 = ldg_l2_256(v + 2);
             uint32_t w[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
 #endif
 #pragma unroll 1
