@@ -226,7 +226,7 @@ __global__ void qs_fill_int_kernel(int* __restrict__ p, size_t n, int v) {
 #define QS_SCORE_PREFETCH 0
 #endif
 #ifndef QS_SCORE_MIN_BLOCKS
-#define QS_SCORE_MIN_BLOCKS 6      // CTAs of 128 threads per SM the compiler must leave room for (80 registers; 4 -> 104 regs is 6 % slower, 8 spills: profiles/r02_a_score_variants.txt)
+#define QS_SCORE_MIN_BLOCKS 6      // CTAs of 128 threads per SM the compiler must leave room for (80 registers; 4 -> 104 regs is 6 % slower, 8 spills: profiles/r01_za_score_variants.txt)
 #endif
 template <typename CINT>
 __global__ void __launch_bounds__(128, QS_SCORE_MIN_BLOCKS) qs_score_table_kernel(const ScoreArgs a) {
@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(128, QS_SCORE_MIN_BLOCKS) qs_score_table_kerne
     const int b = lo;
     // lca(a,b) and its depth for every a < b are the same for the whole block: staged once in shared memory as
     // (inner index | depth << 16).  Read per quartet from global they were a chain of dependent L1 loads and, with the table
-    // reads, half of all warp stalls (profiles/r02_e_*).
+    // reads, half of all warp stalls (profiles/r01_ze_*).
     extern __shared__ uint32_t s_pd[];
     {
         const uint16_t* lrow_g = a.lca + (size_t)b * a.n;
