@@ -340,6 +340,9 @@ def main():
         "kernel": "qs_count_rows_kernel", "kernel_ms": count_ms,
         "dist_kernel_ms": statistics.mean(t["dist_ms"] for t in kt), "score_kernel_ms": statistics.mean(t["score_ms"] for t in kt),
         "peak_source": "measured live on this GPU: HSET2 (fp16x2 compare -> mask) lane-op rate in the kernel's own 2xHSET2+IADD3 mix (qs_measure_alu_peak)",
+        "mix_ceiling": {"frac_of_peak": 0.8, "frac": achieved / (0.8 * hset2_peak),
+                        "note": "the kernel pairs every HSET2 (ALU pipe) with an HADD2 (fp16 FMA pipe); that pair issues at 3.1-3.2 of 4 warp-instr/clk/SM "
+                                "(tools/ubench_pipes.cu, tools/ubench_mix2.cu), i.e. 0.8 of the HSET2 peak is the most this instruction mix can reach"},
         "algorithmic_laneops_per_eval": algo_laneops / my_evals,
         "tree_classes": {"A_fully_resolved": nA, "B_general": nB},
         "per_rank_ms[count,dist,score]": per_rank_ms,
