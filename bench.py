@@ -53,9 +53,9 @@ TABLE_BYTES_LIMIT = 120e9      # a shard's uint16 table above this is not kept r
 HSET2_LANEOPS_PER_EVAL = {"A": 1.0, "B": 1.5}
 INT32_LANEOPS_PER_EVAL = 9.0       # 3 adds + 3 compares + 3 predicated increments
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the counting kernel from the committed `ncu --set full`
-# capture of the same workload on one GPU (profiles/r01_y_count_rows_cfg2_ncu_full.txt: 395.9 MB + 53.1 MB); null where
+# capture of the same workload on one GPU (profiles/r01_zn_count_rows_cfg2_ncu_full.txt: 395.6 MB + 49.6 MB); null where
 # no capture of that exact workload exists
-NCU_DRAM_TRAFFIC_BYTES = {("cfg2", 1): 395905280 + 53114368}
+NCU_DRAM_TRAFFIC_BYTES = {("cfg2", 1): 395583232 + 49617664}
 
 
 def hbm_peak_gbs():
@@ -340,9 +340,9 @@ def main():
         "kernel": "qs_count_rows_kernel", "kernel_ms": count_ms,
         "dist_kernel_ms": statistics.mean(t["dist_ms"] for t in kt), "score_kernel_ms": statistics.mean(t["score_ms"] for t in kt),
         "peak_source": "measured live on this GPU: HSET2 (fp16x2 compare -> mask) lane-op rate in the kernel's own 2xHSET2+IADD3 mix (qs_measure_alu_peak)",
-        "mix_ceiling": {"frac_of_peak": 0.8, "frac": achieved / (0.8 * hset2_peak),
-                        "note": "the kernel pairs every HSET2 (ALU pipe) with an HADD2 (fp16 FMA pipe); that pair issues at 3.1-3.2 of 4 warp-instr/clk/SM "
-                                "(tools/ubench_pipes.cu, tools/ubench_mix2.cu), i.e. 0.8 of the HSET2 peak is the most this instruction mix can reach"},
+        "mix_ceiling": {"frac_of_peak": 0.855, "frac": achieved / (0.855 * hset2_peak),
+                        "note": "the kernel pairs every HSET2 (ALU pipe) with an IMAD.IADD (FMA pipe); that pair issues at 3.42 of 4 warp-instr/clk/SM in isolation "
+                                "(tools/ubench_mix2.cu, profiles/r01_w_ubench_mix2.txt), i.e. 0.855 of the HSET2 peak is the most this instruction mix can reach"},
         "algorithmic_laneops_per_eval": algo_laneops / my_evals,
         "tree_classes": {"A_fully_resolved": nA, "B_general": nB},
         "per_rank_ms[count,dist,score]": per_rank_ms,
@@ -356,7 +356,7 @@ def main():
     line = {
         "metric": "quartet_tree_evals_per_s", "value": nq * m * args.steps / (ms_res * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-        "dtype": "f16x2 compares of exact small integers -> u16x2 integer counters, u16 table, f64 scores", "data": "synthetic",
+        "dtype": "f16x2 compares of exact small integers -> u16x2 integer counters (HSET2 mask + IMAD.IADD), u16 table, f64 scores", "data": "synthetic",
         "config": {"workload": f"{wname}: {w['label']}", "seed": w["seed"], "quartets": nq, "trees": m,
                    "l2": "inputs larger than L2: the distance matrices (%.0f MB) are rebuilt and re-streamed every step" % (2e-6 * n * ((n + 7) // 8 * 8) * m),
                    "parallelism": f"rank-space shards x{world}", "table": "table-free slabs (counted, scanned, discarded)" if table_free else "resident in HBM"},

@@ -3,17 +3,18 @@
 // Four-point test in "fixed pair" form (derivation in count_rows.cuh).  For a fixed taxon pair (p,q) and
 // G_pq(t) = D[q][t] - D[p][t]:   G(u) > G(v)  <=>  the tree displays up|vq.
 //
-// Instruction mix, chosen from measurements on B200 (profiles/r01_b_ubench_pipes.txt,
-// profiles/r01_c_ubench_loop.txt and the ncu captures next to them):
-//   * compare: HSET2.BF.GT / .LT on packed fp16x2 (distances are small integers, exact in fp16): two
-//     quartets per lane, result 1.0 / 0.0 per half.  A missing taxon is NaN -> ordered compare false.
-//     HSET2 runs on the ALU pipe (0.5 warp-instr/clk/SMSP).
-//   * accumulate: HADD2 on the fp16 pipe (0.5 warp-instr/clk/SMSP).  Counters start at -2048 so that a
-//     chunk may hold 4096 trees (fp16 represents every integer in [-2048, 2048] exactly).
-//   The alternative "integer mask + one three-input IADD3 per two masks" needs fewer instructions and looked
-//   better in an isolated microbenchmark, but IADD3 shares the ALU pipe with HSET2: in the real loop ncu
-//   shows pipe_alu at 97 % and 1.22 compares/clk/SM, against 1.46 for HSET2.BF + HADD2 (ALU 79 %,
-//   fp16 83 %, issue 84 %) — so the two half-rate pipes are loaded evenly on purpose.
+// Instruction mix, chosen from measurements on B200 (tools/ubench_pipes.cu, tools/ubench_mix2.cu and the tuning builds timed
+// in profiles/r01_x_*, r01_zm_*):
+//   * compare: HSET2.GT / .LT on packed fp16x2 (distances are small integers, exact in fp16): two quartets per lane, result
+//     an integer mask, 0xFFFF per true half.  A missing taxon is NaN -> ordered compare false.  ALU pipe, half rate.
+//   * accumulate: one TWO-input integer subtract per compare, acc -= mask, which ptxas places on the FMA pipe as
+//     IMAD.IADD.  HSET2 + IMAD.IADD issue at 3.42 of 4 warp-instr/clk/SM in isolation (1.71 compares+accumulates), against
+//     3.10 (1.55) for the fp16 pair HSET2.BF + HADD2 that rounds 1a-1y used, and in the kernel it is 4-6 % faster — provided
+//     the tree loop is NOT unrolled: with two trees per iteration ptxas fuses the two subtracts of a counter into one
+//     three-input IADD3, which runs on the ALU pipe next to the HSET2s and loses 10 % (the "integer counters are slower"
+//     result of rounds 1c and 1x was that fusion).  QS_INT_COUNTERS=0 selects the fp16 pair again.
+//   Subtracting 0xFFFF from a 16-bit half adds 1 to it and borrows 1 from the upper half, so after L low-half and H
+//   high-half hits acc = L + 65536 (H - L) mod 2^32: exact while a chunk holds <= 65535 trees (QS_MAX_CHUNK_TREES = 4096).
 #pragma once
 #include "common.cuh"
 
@@ -22,14 +23,11 @@ namespace qs {
 constexpr int QS_MAX_CHUNK_TREES = 4096;
 
 #ifndef QS_INT_COUNTERS
-#define QS_INT_COUNTERS 0
+#define QS_INT_COUNTERS 1
 #endif
 
 #if QS_INT_COUNTERS
-// Tuning build: integer-mask compare (HSET2 -> 0xFFFF per true half) and a TWO-input integer subtract per compare, which
-// ptxas places on the FMA pipe as IMAD.IADD: 1.71 compares+accumulates/clk/SM in isolation against 1.55 for
-// HSET2.BF + HADD2 (tools/ubench_mix2.cu, profiles/r01_w_ubench_mix2.txt).  Subtracting 0xFFFF from a 16-bit half adds 1
-// to it and borrows 1 from the upper half, so after L low-half and H high-half hits acc = L + 65536 (H - L) mod 2^32.
+// integer-mask compare + two-input subtract (see the header comment)
 typedef uint32_t ctr_t;
 __device__ __forceinline__ ctr_t ctr_zero() { return 0u; }
 #if QS_INT_COUNTERS == 2      // keep every subtract a separate two-input instruction (ptxas otherwise fuses two trees into one IADD3)

@@ -28,7 +28,7 @@
 //   XD  (c; d; diagonal block i, a and b in the same block): all ordered pairs, G(x)>G(y) only;
 //       x<y gives slot 1 of (x,y), x>y gives slot 2 of (y,x) — half the cost of a full block   2 items / thread
 //   Y   (b; c; d-block; a-block): G(a)>G(d)                                                    2 items / thread
-// so a thread always carries 64 packed counter registers and issues 64 HSET2 + 64 HADD2 per tree.  A task
+// so a thread always carries 64 packed counter registers and issues 64 HSET2 + 64 IMAD.IADD per tree.  A task
 // is a run of up to THREADS (512 or 256, see below) thread-items of one kind; consecutive items share matrix rows, and the host records
 // the rows a task touches as at most three contiguous row ranges.  Only those rows are staged per tree
 // (n = 100: ~3 KB instead of the 21 KB matrix; n = 1000: 4 KB for 32,768 quartets = 0.12 B per evaluation).
@@ -82,7 +82,7 @@ struct CountRowsArgs {
 };
 
 #ifndef CR_UNROLL_PF
-#define CR_UNROLL_PF 2          // trees per iteration of the tree loop: 2 is 2.2 % faster than 1 at cfg2 (profiles/r01_r_*)
+#define CR_UNROLL_PF 1          // trees per iteration of the tree loop: must stay 1 with integer counters (count_roles.cuh); 2 was 2 % faster with fp16 counters
 #endif
 #ifndef CR_UNROLL_HALVES
 #define CR_UNROLL_HALVES 1
