@@ -11,7 +11,8 @@
 // as a running minimum while all lanes sweep the same j so that stores go to one matrix row.
 //
 // Output: D[tree][row][col] as IEEE fp16 (exact for integers <= 2048), NaN where either taxon is
-// absent from the tree (the buffer is pre-filled with 0xFFFF = NaN), row pitch n_pad (multiple of 8).
+// absent from the tree (such a tree's matrix is filled with 0xFFFF = NaN before the pair sweep), row pitch n_pad
+// (multiple of 8); the padding columns n..n_pad-1 are never initialised and only ever feed lanes whose results are dropped.
 #pragma once
 #include "common.cuh"
 
@@ -89,6 +90,12 @@ __global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
         __syncthreads();
         const int k = s_k;
         __half* Dt = a.D + (size_t)t * a.n * a.n_pad;
+        if (k < a.n) {                                        // some taxon is absent (or the tree is malformed): NaN everywhere first
+            uint4* w = reinterpret_cast<uint4*>(Dt);          // (a tree that has every taxon writes all n x n entries below, so the
+            const size_t nw16 = (size_t)a.n * a.n_pad / 8;    //  host no longer memsets the whole buffer: 208 MB per step at cfg2)
+            for (size_t x = threadIdx.x; x < nw16; x += blockDim.x) w[x] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            __syncthreads();
+        }
         for (int i0 = 0; i0 < k; i0 += blockDim.x) {
             const int i = i0 + threadIdx.x;
             const bool act = i < k;
@@ -201,6 +208,12 @@ __global__ void __launch_bounds__(32 * DW_WARPS) qs_dist_warp_kernel(DistArgs a)
             a.tree_class[t] = (!bad && k == a.n && maxdeg <= 3) ? 0 : 1;
         }
         __half* Dt = a.D + (size_t)t * a.n * a.n_pad;
+        if (k < a.n) {                                        // absent taxa / malformed tree: NaN everywhere first (see qs_dist_kernel)
+            uint4* w = reinterpret_cast<uint4*>(Dt);
+            const size_t nw16 = (size_t)a.n * a.n_pad / 8;
+            for (size_t x = lane; x < nw16; x += 32) w[x] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+            __syncwarp();
+        }
         for (int i0 = 0; i0 < k; i0 += 32) {
             const int i = i0 + lane;
             const bool act = i < k;

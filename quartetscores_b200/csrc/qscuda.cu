@@ -200,7 +200,7 @@ int run_distances(qs_ctx* c) {
         if ((r = dev_alloc(c, &c->d_order, (size_t)c->m))) { c->class_cap = 0; return r; }
         c->class_cap = c->m;
     }
-    QS_CUDA(c, cudaMemsetAsync(c->d_D, 0xFF, need * sizeof(__half), c->stream));   // 0xFFFF = NaN = "taxon missing"
+    // (no memset of D: the distance kernels write every entry of every matrix, NaN = 0xFFFF = "taxon missing" included)
     QS_CUDA(c, cudaMemsetAsync(c->d_flags, 0, 2 * sizeof(int), c->stream));
     DistArgs da;
     da.node_off = c->d_off; da.parent = c->d_parent; da.leaf_id = c->d_leaf;
