@@ -78,7 +78,7 @@ def test_golden_raw_qic_file(name, golden, tmp_path):
     (40, 300, 11, dict(k_max=10, p_missing=0.1, p_contract=0.1)),
     (50, 1000, 12, dict(k_max=10)),                       # BASELINE config 1 shape
     (64, 257, 13, dict(k_max=30, nni_fraction=0.1)),
-    (9, 2500, 14, dict(k_max=3, p_missing=0.3)),           # more than one fp16 flush chunk
+    (9, 2500, 14, dict(k_max=3, p_missing=0.3)),           # more than one tree chunk per task
     (33, 100, 15, dict(k_max=5, p_contract=0.5)),
 ])
 def test_counts_vs_oracle_seeded(n, m, seed, kw):
@@ -140,7 +140,7 @@ def test_bad_tree_encoding_rejected(golden):
 
 @pytest.mark.parametrize("n,m,seed,kw", [
     (70, 120, 32, dict(k_max=15)),                          # several variable rows per task, class A only
-    (19, 4300, 33, dict(k_max=4, p_missing=0.2)),          # > 4096 trees: more than one fp16 counter chunk, class B
+    (19, 4300, 33, dict(k_max=4, p_missing=0.2)),          # > 4096 trees: more than one counter chunk (QS_MAX_CHUNK_TREES), class B
     (21, 4500, 34, dict(k_max=4)),                          # > 4096 class-A trees
     (130, 40, 35, dict(k_max=25, p_missing=0.05, p_contract=0.05)),   # wider rows, tasks that split a row's items
 ])
