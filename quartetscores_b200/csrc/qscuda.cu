@@ -430,7 +430,7 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
     a.max_tps = CR_MAX_TPS; a.max_stages = CR_MAX_STAGES;
     if (const char* env = getenv("QS_MAX_TPS")) a.max_tps = std::max(1, std::min(32, atoi(env)));             // tuning hooks
     if (const char* env = getenv("QS_MAX_STAGES")) a.max_stages = std::max(2, std::min((int)CR_MAX_STAGES, atoi(env)));
-    // tree chunks: <= 4096 trees (fp16 counters) and >= 256; among the chunk counts that give the dynamic scheduler
+    // tree chunks: <= QS_MAX_CHUNK_TREES = 4096 trees (the chunk's tree ids live in shared memory) and >= 256; among the chunk counts that give the dynamic scheduler
     // 3..16 tasks per SM pick the smallest one whose last round of tasks is (nearly) the fullest
     const bool all_a = c->n_class_a == c->m;
     const int64_t base = std::max<int64_t>(1, (int64_t)a.n_x + (all_a ? 0 : a.n_y));
