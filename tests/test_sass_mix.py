@@ -1,0 +1,41 @@
+"""The counting kernel's speed depends on what ptxas makes of `acc -= mask`: a two-input IMAD.IADD (FMA pipe) next to
+every HSET2 (ALU pipe).  If the tree loop is unrolled, ptxas fuses the two subtracts of a counter into one three-input
+IADD3 on the ALU pipe and the kernel loses 10 %.  This guards the property on the built library;
+it needs cuobjdump (CUDA toolkit), not a GPU."""
+import os
+import re
+import shutil
+import subprocess
+
+import pytest
+
+from quartetscores_b200 import _ffi
+
+
+def kernel_sass(pattern):
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([exe, "-sass", _ffi.LIB_PATH], capture_output=True, text=True, timeout=300).stdout
+    chunks = re.split(r"\n\s*Function : ", out)
+    for ch in chunks:
+        if re.match(pattern, ch):
+            return [l.split(";")[0].strip() for l in ch.splitlines() if re.match(r"\s*/\*[0-9a-f]{4,}\*/", l)]
+    pytest.fail(f"no kernel matching {pattern} in {_ffi.LIB_PATH}")
+
+
+@pytest.mark.parametrize("threads", [512, 256])
+def test_counting_loop_pairs_every_hset2_with_an_imad_iadd(threads):
+    lines = kernel_sass(rf"_ZN2qs20qs_count_rows_kernelILi{threads}EEEvNS_13CountRowsArgsE")
+    lt = [i for i, l in enumerate(lines) if "HSET2.LT" in l]
+    assert lt, "role-X loop (HSET2.LT) not found"
+    # the role-X tree loop: the instructions around its HSET2.LT compares, up to the backward branch that closes it
+    lo = lt[0] - 40
+    hi = next(i for i in range(lt[-1], len(lines)) if " BRA " in lines[i] + " ")
+    body = lines[max(lo, 0):hi]
+    n_hset = sum("HSET2" in l for l in body)
+    n_sub = sum("IMAD.IADD" in l and ", -R" in l for l in body)
+    fused = [l for l in body if "IADD3" in l and l.count(", -R") >= 2]
+    assert n_hset >= 64 and n_sub >= n_hset, (n_hset, n_sub)        # 64 packed compares (128 quartet-slot compares) per thread and tree
+    assert not fused, fused[:3]
+    assert not any(op in l for l in body for op in ("HADD2.F32", "STL", "LDL")), "spills or conversions inside the tree loop"
