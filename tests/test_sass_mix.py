@@ -39,3 +39,10 @@ def test_counting_loop_pairs_every_hset2_with_an_imad_iadd(threads):
     assert n_hset >= 64 and n_sub >= n_hset, (n_hset, n_sub)        # 64 packed compares (128 quartet-slot compares) per thread and tree
     assert not fused, fused[:3]
     assert not any(op in l for l in body for op in ("HADD2.F32", "STL", "LDL")), "spills or conversions inside the tree loop"
+
+
+def test_counting_kernel_stages_rows_with_tma_bulk_copies():
+    lines = kernel_sass(r"_ZN2qs20qs_count_rows_kernelILi512EEEvNS_13CountRowsArgsE")
+    assert any(l.split()[1].startswith("UBLKCP") or " UBLKCP" in l for l in lines), "cp.async.bulk (UBLKCP) missing: rows are no longer staged by TMA"
+    assert any("SYNCS.PHASECHK" in l for l in lines) and any("SYNCS.ARRIVE" in l for l in lines), "mbarrier pipeline missing"
+    assert sum("LDS.128" in l for l in lines) >= 8
