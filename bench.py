@@ -152,9 +152,25 @@ def reference_sample_size(w, target_evals):
     return max(256, min(w["n_trees"], s))    # >= 256 trees keeps CINT = uint16 (src/QuartetScores.cpp:115-123)
 
 
+REFERENCE_MAX_QUARTETS = 5e7      # the reference's scoring pass visits every quartet under a critical section (5.8 s for 3.9e6 at cfg2):
+                                   # at 500 taxa (2.6e9 quartets) one run takes hours whatever the tree sample, so it is not attempted
+
+
+def reference_infeasible(w):
+    nq = comb(w["n_taxa"], 4)
+    if nq <= REFERENCE_MAX_QUARTETS:
+        return None
+    return (f"the reference binary is not run on this workload: its scoring pass is serialised over all {nq:.3g} quartets "
+            f"(about {5.8 * nq / 3.9e6 / 3600:.1f} h at the cfg2 rate) and no tree sample shortens it; cfg2 is the workload both arms can run")
+
+
 def reference_arm(args, w, wname):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return 0
+    why = reference_infeasible(w)
+    if why:
+        print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
         return 0
     cores = os.cpu_count() or 1
     sample = reference_sample_size(w, 2.0e9)
@@ -368,7 +384,9 @@ def main():
         "roofline": roofline,
     }
 
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline and reference_infeasible(w):
+        line["cpu_baseline"] = {"value": None, "unit": "evals/s", "cores": 0, "kind": "reference", "sample": reference_infeasible(w)}
+    elif rank == 0 and not args.no_cpu_baseline:
         # reference binary on this box's host cores, bounded sample of the same workload
         try:
             cores = os.cpu_count() or 1
