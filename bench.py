@@ -20,6 +20,7 @@ per-node-pair topology sums (NCCL).  The job is fixed as N grows: "scaling": "st
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import re
@@ -55,7 +56,7 @@ INT32_LANEOPS_PER_EVAL = 9.0       # 3 adds + 3 compares + 3 pre
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the counting kernel from the committed `ncu --set full`
 # capture of the same workload on one GPU (profiles/r01_zn_count_rows_cfg2_ncu_full.txt: 395.6 MB + 49.6 MB); null where
 # no capture of that exact workload exists
-NCU_DRAM_TRAFFIC_BYTES = {("cfg2", 1): 395583232 + 49617664}
+NCU_DRAM_TRAFFIC = {("cfg2", 1): {"bytes": 395583232 + 49617664, "source": "profiles/r01_zn_count_rows_cfg2_ncu_full.txt", "not_this_run": True}}
 
 
 def hbm_peak_gbs():
@@ -165,6 +166,8 @@ def reference_infeasible(w):
 
 
 def reference_arm(args, w, wname):
+    """The UNMODIFIED reference binary on the WHOLE workload (no tree sample, no extrapolation): one warm-up run and
+    min(steps, 2) timed runs -- a cfg2 run takes about a minute on 16 cores, so --steps/--warmup beyond that are ignored."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -173,31 +176,31 @@ def reference_arm(args, w, wname):
         print(json.dumps({"impl": "reference", "unavailable": why}), flush=True)
         return 0
     cores = os.cpu_count() or 1
-    sample = reference_sample_size(w, 2.0e9)
-    inp = make_input(dict(w, n_trees=sample), want_newick=True)
+    m = w["n_trees"]
+    inp = make_input(w, want_newick=True)
     nq = comb(w["n_taxa"], 4)
+    n_warm, n_timed = min(args.warmup, 1), max(1, min(args.steps, 2))
     times, parts = [], []
     kind = "?"
     with tempfile.TemporaryDirectory() as tmp:
-        for i in range(args.warmup + args.steps):
+        for i in range(n_warm + n_timed):
             el, cnt, sc, kind = run_reference_binary(inp.ref_newick, inp.eval_newick, cores, tmp, "r")
-            if i >= args.warmup:
+            if i >= n_warm:
                 times.append(el)
                 parts.append((cnt, sc))
-    total = sum(times)
-    sample_value = nq * sample * len(times) / total
     mean = lambda xs: sum(xs) / len(xs)
-    value, full_s = reference_full_estimate(nq, w["n_trees"], sample, mean(times), mean([p[0] for p in parts]), mean([p[1] for p in parts]))
+    value = nq * m / mean(times)
     line = {
-        "impl": "reference", "metric": "quartet_tree_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "impl": "reference", "metric": "quartet_tree_evals_per_s", "value": value, "unit": "evals/s", "n_gpus": args.gpus, "steps": n_timed,
+        "warmup": n_warm, "ms_per_step": 1e3 * mean(times), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u16", "data": "synthetic",
-        "config": {"workload": f"{wname}: {w['label']}", "sample": f"first {sample} of {w['n_trees']} gene trees per step"},
-        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference", "sample_value": sample_value,
-                         "sample": f"oracle/_ref/QuartetScores -t {cores}, {kind} table, first {sample} of {w['n_trees']} trees per step: {mean(times):.2f} s end-to-end "
-                                   f"({mean([p[0] for p in parts]):.2f} s counting, {mean([p[1] for p in parts]):.2f} s scoring); value = whole-workload estimate "
-                                   f"({full_s:.1f} s: counting and parsing scaled by the tree count, scoring constant); the sample's own throughput is sample_value"},
+        "config": {"workload": f"{wname}: {w['label']}", "seed": w["seed"], "quartets": nq, "trees": m,
+                   "note": f"whole workload every step; {n_warm} warm-up + {n_timed} timed runs (a run takes about a minute: --steps/--warmup beyond that are ignored)"},
+        "cpu_baseline": {"value": value, "unit": "evals/s", "cores": cores, "kind": "reference",
+                         "sample": f"oracle/_ref/QuartetScores -t {cores}, {kind} table, ALL {m} gene trees (no sample, no extrapolation): {mean(times):.2f} s end-to-end "
+                                   f"({mean([p[0] for p in parts]):.2f} s counting, {mean([p[1] for p in parts]):.2f} s scoring), Newick files in, annotated Newick out"},
         "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "e2e_cli": {"seconds": mean(times), "what": f"oracle/_ref/QuartetScores -r ref.nwk -e eval.nwk -o out.nwk -t {cores}: the binary's own 'Elapsed time'"},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
@@ -207,6 +210,71 @@ def reference_arm(args, w, wname):
 # -------------------------------------------------------------------------------------------------
 # our arm
 # -------------------------------------------------------------------------------------------------
+
+GOLDEN_BIG = {"cfg1": "cfg1_50x1000", "cfg2": "cfg2_100x10000"}
+
+
+def _load_golden(wname, w):
+    import numpy as np
+
+    path = os.path.join(ROOT, "tests", "golden", "big", GOLDEN_BIG.get(wname, "-") + ".npz")
+    if not os.path.exists(path):
+        return None, None
+    z = np.load(path)
+    spec = json.loads(z["spec"].item())
+    if any(spec.get(k) != w.get(k) for k in ("n_taxa", "n_trees", "seed", "k_max")):
+        return None, None
+    return z, path
+
+
+def golden_check(wname, w, scores):
+    """Compare this run's scores with the unmodified reference's on the same input (committed digest), where one exists."""
+    import numpy as np
+
+    z, path = _load_golden(wname, w)
+    if z is None:
+        return None
+    worst, same_inf = 0.0, True
+    for got, key in zip(scores, ("lqic", "qpic", "eqpic")):
+        want = z[key]
+        same_inf = same_inf and bool(np.array_equal(np.isinf(got), np.isinf(want)))
+        fin = np.isfinite(want) & np.isfinite(got)
+        if fin.any():
+            worst = max(worst, float(np.abs(got[fin] - want[fin]).max()))
+    return {"file": os.path.relpath(path, ROOT), "reference": "oracle/_ref/qs_ref_dump (unmodified reference headers), fast table",
+            "scores_within_1e-9": bool(same_inf and worst <= 1e-9), "max_abs_diff": worst}
+
+
+def cli_end_to_end(w, wname):
+    """End-to-end seconds of the drop-in CLI: the reference's own main linked against libqscuda.so
+    (oracle/_ref/QuartetScoresB200, integration/main_b200.cpp): Newick files in, annotated Newick out, process start and
+    CUDA context creation included.  The reference binary's number for the same files is the reference arm's e2e_cli."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "QuartetScoresB200")
+    if not os.path.exists(exe):
+        return {"seconds": None, "what": "oracle/_ref/QuartetScoresB200 not built (needs /root/reference at build time)"}
+    try:
+        inp = make_input(w, want_newick=True)
+        z, _ = _load_golden(wname, w)
+        runs = []
+        with tempfile.TemporaryDirectory() as tmp:
+            rp, ep = os.path.join(tmp, "ref.nwk"), os.path.join(tmp, "eval.nwk")
+            inp.write(rp, ep)
+            same = None
+            for i in range(3):
+                op = os.path.join(tmp, f"out{i}.nwk")
+                t0 = time.time()
+                out = subprocess.run([exe, "-r", rp, "-e", ep, "-o", op, "-t", str(os.cpu_count() or 1)], capture_output=True, text=True, check=True).stdout
+                wall = time.time() - t0
+                el = re.search(r"Elapsed time: (\d+) microseconds", out)
+                runs.append({"wall_s": round(wall, 4), "elapsed_s": int(el.group(1)) * 1e-6 if el else None})
+                if z is not None:
+                    same = open(op).read() == z["out_newick"].item()
+        return {"seconds": min(r["wall_s"] for r in runs), "runs": runs, "output_identical_to_reference": same,
+                "what": "wall clock of `oracle/_ref/QuartetScoresB200 -r ref.nwk -e eval.nwk -o out.nwk` (fork to exit: process start, CUDA context, "
+                        "Newick ingest, counting, scoring, writing); best of 3, every run listed; elapsed_s is the binary's own 'Elapsed time' line"}
+    except Exception as e:
+        return {"seconds": None, "what": f"failed: {e}"}
+
 
 def main():
     ap = argparse.ArgumentParser()
@@ -221,7 +289,12 @@ def main():
     if args.impl == "ours" and not args.no_e2e:
         args.warmup = max(args.warmup, 3)       # timing rule: W >= 3 (exploration runs with --no-e2e may use fewer)
 
-    wname = args.workload or "cfg2"
+    # Default workload: the plain single-process run (the driver's BENCH, N = 1) times BASELINE configs[1] (cfg2), the one
+    # configuration the reference binary also runs in minutes, so both arms share it.  A run launched through
+    # torch.distributed.run (the driver's 1/2/4/8 scaling runs, N = 1 included) times configs[2] (cfg3), the configuration
+    # BASELINE.json lists "at 1/2/4/8 B200": a 5 ms cfg2 step cannot show how rank-space shards scale.
+    under_torchrun = "TORCHELASTIC_RUN_ID" in os.environ or "WORLD_SIZE" in os.environ
+    wname = args.workload or ("cfg3" if under_torchrun else "cfg2")
     w = WORKLOADS[wname]
     if args.impl == "reference":
         try:
@@ -352,7 +425,7 @@ def main():
     achieved = algo_laneops / (count_ms * 1e-3)
     roofline = {
         "bound": "alu_issue", "achieved": achieved / 1e12, "peak": hset2_peak / 1e12, "unit": "Tlaneop/s", "frac": achieved / hset2_peak,
-        "traffic": NCU_DRAM_TRAFFIC_BYTES.get((wname, world)),
+        "traffic": NCU_DRAM_TRAFFIC.get((wname, world)),      # ncu DRAM bytes of one launch from a committed capture (never measured by this run), else null
         "kernel": "qs_count_rows_kernel", "kernel_ms": count_ms,
         "dist_kernel_ms": statistics.mean(t["dist_ms"] for t in kt), "score_kernel_ms": statistics.mean(t["score_ms"] for t in kt),
         "peak_source": "measured live on this GPU: HSET2 (fp16x2 compare -> mask) lane-op rate in the kernel's own 2xHSET2+IADD3 mix (qs_measure_alu_peak)",
@@ -369,6 +442,15 @@ def main():
                 "note": "table written once + distance matrices read once; the path is ALU-bound by three orders of magnitude (traffic = ncu DRAM bytes of one launch)"},
     }
 
+    # checksum of the three score vectors (bit patterns): must be the same at every N (integer sums and exact minima do not
+    # depend on how the rank space is sharded), and for cfg1/cfg2 the scores are compared with the unmodified reference's
+    # (tests/golden/big/*.npz, generated by tests/golden/make_golden_big.py from oracle/_ref)
+    scores_sha256 = hashlib.sha256(b"".join(np.ascontiguousarray(x, np.float64).tobytes() for x in scores)).hexdigest()
+    golden = golden_check(wname, w, scores)
+    cli = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not reference_infeasible(w):
+        cli = cli_end_to_end(w, wname)
+
     line = {
         "metric": "quartet_tree_evals_per_s", "value": nq * m * args.steps / (ms_res * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -380,6 +462,9 @@ def main():
             "value": nq * m * args.steps / (ms_e2e * 1e-3), "unit": "evals/s", "ms_per_step": ms_e2e / args.steps,
             "h2d_bytes_per_step": int(h_off.numel() * 8 + h_par.numel() * 4 + h_leaf.numel() * 4), "d2h_bytes_per_step": int(3 * E * 8)},
         "gpu_launches": int(launches),
+        "scores_sha256": scores_sha256,
+        "golden": golden,
+        "e2e_cli": cli,
         "clocks": clocks,
         "roofline": roofline,
     }

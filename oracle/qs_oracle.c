@@ -267,6 +267,63 @@ int qso_count_fourpoint(int n_taxa, int n_trees, const int64_t* node_off, const 
     return 0;
 }
 
+/* Sampled restatement for sizes where the whole table is out of reach (n = 500 .. 2000): the entries of the given
+ * ranks only.  A rank is unranked by inverting quartet_lookup_table.hpp:141-168 (largest s3 with C(s3,4) <= r, then
+ * s2, s1, s0); per tree the six leaf-to-leaf distances are TreeInformation.hpp:40-43 evaluated by plain climbing, and the
+ * topology is the unique minimum of the three pair sums.  out[i*3 + slot], caller zeroes it. */
+void qso_unrank(uint64_t r, uint64_t q[4]) {
+    uint64_t s3 = 3;
+    while ((s3 + 1) * s3 * (s3 - 1) * (s3 - 2) / 24 <= r) ++s3;
+    r -= s3 * (s3 - 1) * (s3 - 2) * (s3 - 3) / 24;
+    uint64_t s2 = 2;
+    while ((s2 + 1) * s2 * (s2 - 1) / 6 <= r) ++s2;
+    r -= s2 * (s2 - 1) * (s2 - 2) / 6;
+    uint64_t s1 = 1;
+    while ((s1 + 1) * s1 / 2 <= r) ++s1;
+    r -= s1 * (s1 - 1) / 2;
+    q[0] = r; q[1] = s1; q[2] = s2; q[3] = s3;
+}
+
+int qso_count_fourpoint_ranks(int n_taxa, int n_trees, const int64_t* node_off, const int32_t* parent, const int32_t* leaf_id,
+                              int64_t n_ranks, const uint64_t* ranks, uint32_t* out) {
+    int* quads = (int*)malloc((size_t)n_ranks * 4 * sizeof(int));
+    int* leaf_of = (int*)malloc((size_t)n_taxa * sizeof(int));
+    for (int64_t i = 0; i < n_ranks; ++i) {
+        uint64_t q[4];
+        qso_unrank(ranks[i], q);
+        if (q[3] >= (uint64_t)n_taxa || !(q[0] < q[1] && q[1] < q[2] && q[2] < q[3]) || rank_sorted(q[0], q[1], q[2], q[3]) != ranks[i]) { free(quads); free(leaf_of); return -5; }
+        for (int k = 0; k < 4; ++k) quads[i * 4 + k] = (int)q[k];
+    }
+    int rc = 0;
+    for (int t = 0; t < n_trees && rc == 0; ++t) {
+        const int N = (int)(node_off[t + 1] - node_off[t]);
+        const int32_t* lid = leaf_id + node_off[t];
+        otree T;
+        if (otree_build(&T, N, parent + node_off[t], lid, NULL) != 0) { otree_free(&T); rc = -1; break; }
+        for (int i = 0; i < n_taxa; ++i) leaf_of[i] = -1;
+        for (int i = 0; i < T.k; ++i) {
+            const int v = T.leaf_seq[i];
+            if (lid[v] < 0 || lid[v] >= n_taxa) { rc = -2; break; }
+            leaf_of[lid[v]] = v;
+        }
+        if (rc == 0) {
+#pragma omp parallel for schedule(static)
+            for (int64_t i = 0; i < n_ranks; ++i) {
+                const int a = leaf_of[quads[i * 4]], b = leaf_of[quads[i * 4 + 1]], c = leaf_of[quads[i * 4 + 2]], d = leaf_of[quads[i * 4 + 3]];
+                if (a < 0 || b < 0 || c < 0 || d < 0) continue;
+                const unsigned s0 = dist_edges(&T, a, b) + dist_edges(&T, c, d), s1 = dist_edges(&T, a, c) + dist_edges(&T, b, d),
+                               s2 = dist_edges(&T, a, d) + dist_edges(&T, b, c);
+                if (s0 < s1 && s0 < s2) out[i * 3 + 0]++;
+                else if (s1 < s0 && s1 < s2) out[i * 3 + 1]++;
+                else if (s2 < s0 && s2 < s1) out[i * 3 + 2]++;
+            }
+        }
+        otree_free(&T);
+    }
+    free(quads); free(leaf_of);
+    return rc;
+}
+
 /* ------------------------------------------------------------------------------------------ */
 /* scoring                                                                                     */
 /* ------------------------------------------------------------------------------------------ */

@@ -55,6 +55,14 @@ int qso_count_clades_fast(int n_taxa, int n_trees, const int64_t* node_off, cons
 int qso_count_fourpoint(int n_taxa, int n_trees, const int64_t* node_off, const int32_t* parent,
                         const int32_t* leaf_id, uint32_t* table);
 
+/* The same four-point restatement for a SAMPLE of table entries (sizes where C(n,4) entries are out of reach for a
+ * CPU checker): out[i*3 + slot] = canonical count of the quartet with rank ranks[i] (quartet_lookup_table.hpp:141-212
+ * inverted by qso_unrank -> q[0] < q[1] < q[2] < q[3]); distances by climbing to the LCA (TreeInformation.hpp:40-43).
+ * Caller zeroes out.  Returns 0, <0 on a malformed tree or a rank outside C(n_taxa,4). */
+void qso_unrank(uint64_t rank, uint64_t q[4]);
+int qso_count_fourpoint_ranks(int n_taxa, int n_trees, const int64_t* node_off, const int32_t* parent, const int32_t* leaf_id,
+                              int64_t n_ranks, const uint64_t* ranks, uint32_t* out);
+
 /* QuartetScoreComputer.hpp:135-159, same operation order, libm log. */
 double qso_log_score(uint64_t q1, uint64_t q2, uint64_t q3);
 

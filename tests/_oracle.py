@@ -82,6 +82,26 @@ def count_fourpoint(n_taxa, flat):
     return _count(lib().qso_count_fourpoint, n_taxa, flat)
 
 
+def unrank(r):
+    q = (C.c_uint64 * 4)()
+    lib().qso_unrank(C.c_uint64(int(r)), q)
+    return tuple(int(x) for x in q)
+
+
+def count_fourpoint_ranks(n_taxa, flat, ranks):
+    """Canonical counts of the table entries `ranks` only (uint32 [len(ranks), 3]) -- for n where C(n,4) is out of reach."""
+    off = np.ascontiguousarray(flat.node_offsets, np.int64)
+    par = np.ascontiguousarray(flat.parent, np.int32)
+    leaf = np.ascontiguousarray(flat.leaf_lookup_id, np.int32)
+    ranks = np.ascontiguousarray(ranks, np.uint64)
+    out = np.zeros((len(ranks), 3), np.uint32)
+    r = lib().qso_count_fourpoint_ranks(n_taxa, len(off) - 1, _p(off, C.c_int64), _p(par, C.c_int32), _p(leaf, C.c_int32),
+                                        C.c_int64(len(ranks)), _p(ranks, C.c_uint64), _p(out, C.c_uint32))
+    if r != 0:
+        raise RuntimeError(f"qso_count_fourpoint_ranks failed: {r}")
+    return out
+
+
 def score(ref, table, count_scale=1, cint_bits=16):
     """ref: newick.FlatReference; table: canonical counts uint32[C(n,4),3].
     Returns (lqic, qpic, eqpic, bifurcating)."""
