@@ -96,7 +96,9 @@ int qs_num_trees(const qs_ctx* ctx, int64_t* n_trees);
 /* Replaces: QuartetCounterLookup::countQuartets + updateQuartets* (QuartetCounterLookup.hpp:66-238) and
  * the TreeInformation distance queries (TreeInformation.hpp:40-43) applied per gene tree.
  * Builds every tree's n x n distance matrix on the device and counts, for every quartet of this
- * shard and every tree, the displayed topology.  QS_MODE_TABLE leaves the table resident;
+ * shard and every tree, the displayed topology.  Limit: distances are held as exact small integers in fp16, so a gene
+ * tree with a leaf-to-leaf path longer than 2,048 edges is refused with QS_E_UNSUPPORTED (the reference's distances are
+ * `unsigned`, TreeInformation.hpp:40-43; such a tree needs more than 2,049 taxa or long chains of unary nodes).  QS_MODE_TABLE leaves the table resident;
  * QS_MODE_TABLE_FREE also accumulates the scoring partials (qs_count then implies the scan). */
 int qs_count(qs_ctx* ctx);
 
@@ -104,7 +106,9 @@ int qs_count(qs_ctx* ctx);
  * (QuartetScoreComputer.hpp:379-593) and getLQICScores/getQPICScores/getEQPICScores (:106-126).
  * Each output has edge_count = n_nodes-1 doubles indexed by genesis edge index, +inf where untouched
  * (:763,772-774).  For a multifurcating reference only lqic is computed; qpic/eqpic (may be NULL) are
- * filled with +inf.  count_scale: 1 = the reference's runtime-efficient table semantics, 2 = its
+ * filled with +inf.  Limit: the LQ-IC selection packs three counts into 63 bits, so n_trees * count_scale must stay below
+ * 2^21 (2,097,152) — beyond that qs_score fails with QS_E_UNSUPPORTED (the reference's log_score takes size_t and has
+ * no such limit; QuartetScoreComputer.hpp:135).  count_scale: 1 = the reference's runtime-efficient table semantics, 2 = its
  * memory-efficient (-s) table, whose stored counts are doubled and wrap in CINT;
  * the 32-bit wrap of the QP-IC accumulators (QuartetScoreComputer.hpp:382) is always reproduced unless
  * exact_qp != 0.  With shard_count > 1 this returns the scores of this shard's quartets only; use
@@ -119,6 +123,24 @@ int qs_score_num_pairs(const qs_ctx* ctx, int64_t* n_pairs);
 int qs_score_partials(qs_ctx* ctx, int count_scale, double* lqic_partial, uint64_t* pair_sums);
 int qs_score_finalize(qs_ctx* ctx, int exact_qp, const double* lqic_reduced, const uint64_t* pair_sums_reduced,
                       double* lqic, double* qpic, double* eqpic);
+
+/* Multi-GPU without the host in the data path (one process per GPU; NCCL over NVLink).  The per-inner-node-pair
+ * partials stay on the device and the CALLER's collectives run on them in place, on the context's stream:
+ *   qs_score_scan(ctx, count_scale)              scan this shard's table (table-free contexts: already done by qs_count);
+ *                                                asynchronous, nothing is copied to the host
+ *   qs_score_device_partials(...)                device pointers, n_pairs elements each (x3 for pair_sums), all int64-compatible:
+ *        pair_sums   uint64 [n_pairs][3]  topology sums (QuartetScoreComputer.hpp:429-431)            -> all-reduce SUM
+ *        pair_score  int64  [n_pairs]     order-preserving image of the pair's minimal QIC (:432), max = none -> all-reduce MIN
+ *        pair_best   int64  [n_pairs]     count triple of the quartet that attains it, max = none
+ *   qs_score_select_winners(ctx)                 after the MIN all-reduce of pair_score: shards that do not hold the
+ *                                                winning score drop their triple                          -> all-reduce MIN of pair_best
+ *   qs_score_finish(ctx, exact_qp, lqic, qpic, eqpic)   per-edge minima on the device, log_score of the selected triples / sums
+ *                                                on the host (libm, reference operation order); same outputs as qs_score.
+ * With one shard, qs_score == qs_score_scan + qs_score_finish.  Replaces the same reference lines as qs_score. */
+int qs_score_scan(qs_ctx* ctx, int count_scale);
+int qs_score_device_partials(qs_ctx* ctx, void** pair_sums, void** pair_score, void** pair_best, int64_t* n_pairs);
+int qs_score_select_winners(qs_ctx* ctx);
+int qs_score_finish(qs_ctx* ctx, int exact_qp, double* lqic, double* qpic, double* eqpic);
 
 /* Parity hook for QuartetCounterLookup::countQuartetOccurrences (QuartetCounterLookup.hpp:300-318):
  * canonical per-tree counts (1 per tree) of the entries [rank_begin, rank_end) in table layout, 3*cint_bytes

@@ -40,6 +40,10 @@ SIGNATURES = {
     "qs_score_num_pairs": (C.c_int, [C.c_void_p, _i64p]),
     "qs_score_partials": (C.c_int, [C.c_void_p, C.c_int, _f64p, _u64p]),
     "qs_score_finalize": (C.c_int, [C.c_void_p, C.c_int, _f64p, _u64p, _f64p, _f64p, _f64p]),
+    "qs_score_scan": (C.c_int, [C.c_void_p, C.c_int]),
+    "qs_score_device_partials": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64p]),
+    "qs_score_select_winners": (C.c_int, [C.c_void_p]),
+    "qs_score_finish": (C.c_int, [C.c_void_p, C.c_int, _f64p, _f64p, _f64p]),
     "qs_get_counts": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "qs_shard_range": (C.c_int, [C.c_void_p, _u64p, _u64p]),
     "qs_shard_bounds": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _u64p, _u64p]),

@@ -43,7 +43,7 @@ class Context:
         if rc != 0:
             raise _ffi.QSError(rc, "qs_create: " + self._lib.qs_strerror(rc).decode())
         self.n_taxa, self.cint_bytes, self.mode = n_taxa, cint_bytes, mode
-        self.shard_index, self.shard_count = shard_index, shard_count
+        self.shard_index, self.shard_count, self.device = shard_index, shard_count, device
         self.edge_count = 0
         self.bifurcating_hint = None
 
@@ -148,6 +148,25 @@ class Context:
         lq, qp, eqp = (np.empty(E, np.float64) for _ in range(3))
         self._check(self._lib.qs_score_finalize(self._h, int(exact_qp), _ptr(lqr, C.c_double), _ptr(ps, C.c_uint64), _ptr(lq, C.c_double),
                                                 _ptr(qp, C.c_double), _ptr(eqp, C.c_double)), "qs_score_finalize")
+        return lq, qp, eqp
+
+    # ---- multi-GPU, device-resident partials (include/qscuda.h) ----
+    def score_scan(self, count_scale: int = 1):
+        self._check(self._lib.qs_score_scan(self._h, count_scale), "qs_score_scan")
+
+    def score_device_partials(self):
+        """(pair_sums_ptr, pair_score_ptr, pair_best_ptr, n_pairs): raw device addresses of this context's partials."""
+        a, b, c, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._check(self._lib.qs_score_device_partials(self._h, C.byref(a), C.byref(b), C.byref(c), C.byref(n)), "qs_score_device_partials")
+        return a.value, b.value, c.value, n.value
+
+    def score_select_winners(self):
+        self._check(self._lib.qs_score_select_winners(self._h), "qs_score_select_winners")
+
+    def score_finish(self, exact_qp: bool = False):
+        E = self.edge_count
+        lq, qp, eqp = (np.empty(E, np.float64) for _ in range(3))
+        self._check(self._lib.qs_score_finish(self._h, int(exact_qp), _ptr(lq, C.c_double), _ptr(qp, C.c_double), _ptr(eqp, C.c_double)), "qs_score_finish")
         return lq, qp, eqp
 
     def shard_range(self):

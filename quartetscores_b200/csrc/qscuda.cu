@@ -35,6 +35,7 @@ using namespace qs;
 namespace {
 
 constexpr int kMaxHalfExact = 2048;     // integers up to 2048 are exact in fp16 (distances; the counters are integer)
+constexpr size_t kTableSlack = 64;      // the scan reads the table in 48-byte groups: the last one may reach past the last entry
 
 struct HostRef {
     int n_nodes = 0, n_inner = 0;
@@ -42,6 +43,9 @@ struct HostRef {
     std::vector<int32_t> parent, parent_edge, leaf_id, first_child, next_sib, depth, inner_index, inner_node, leaf_node;
     std::vector<uint16_t> lca;          // [n][n] inner index
     std::vector<uint16_t> idepth;       // [I]
+    // scan kernel (kernels/score.cuh): rows of lca[][] run-length encoded, parents in inner-index space
+    std::vector<uint32_t> run_off, run_end, run_pd;
+    std::vector<int32_t> inner_parent, leaf_parent;
 };
 
 }  // namespace
@@ -56,14 +60,20 @@ struct qs_ctx {
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int64_t launches = 0;
     double dist_ms = 0, count_ms = 0, score_ms = 0;
+    bool score_timed = false;            // ev[4]/ev[5] bracket a scan whose time has not been read yet
 
     bool has_ref = false;
     HostRef ref;
     uint16_t* d_lca = nullptr;
     uint16_t* d_idepth = nullptr;
-    int64_t* d_PB = nullptr;
-    int64_t score_blocks = 0;
-    int score_dB = -1, score_dE = -1;
+    uint32_t *d_run_off = nullptr, *d_run_end = nullptr, *d_run_pd = nullptr;
+    int32_t *d_inner_parent = nullptr, *d_leaf_parent = nullptr;
+    int32_t *d_inner_node = nullptr, *d_node_parent = nullptr, *d_node_depth = nullptr, *d_node_edge = nullptr, *d_node_inner = nullptr;
+    long long* d_edge = nullptr;          // [4][E] edge minima / arg-minima of the per-edge reduction
+    unsigned long long* d_edge_out = nullptr;   // [E][7]
+    unsigned long long* d_scan_scratch = nullptr;
+    size_t scan_scratch_bytes = 0;
+    int* d_scan_counter = nullptr;
 
     // trees
     int64_t m = 0, total_nodes = 0, cap_nodes = 0, cap_trees = 0;
@@ -97,12 +107,14 @@ struct qs_ctx {
     bool counted_once = false;   // n_class_a holds the class split of an earlier qs_count on this context
 
     // scoring
-    unsigned long long* d_pair_sums = nullptr;
-    unsigned long long* d_pair_best = nullptr;
-    int* d_pair_hint = nullptr;
-    std::vector<unsigned long long> h_pair_sums, h_pair_best;
+    unsigned long long* d_pair_sums = nullptr;      // [I*I][3]
+    long long* d_pair_best = nullptr;               // [I*I] packed triple
+    long long* d_pair_score = nullptr;              // [I*I] ordered image of the exact score of pair_best (all-reduced MIN across shards)
+    long long* d_pair_score_local = nullptr;        // [I*I] this shard's own copy (qs_score_select_winners)
+    std::vector<unsigned long long> h_pair_sums, h_edge_out;
     bool fused_partials_valid = false;   // table-free mode: partials accumulated by qs_count
     int fused_scale = 1;
+    bool partials_ready = false;         // the device partials hold a finished scan (qs_score_scan / table-free qs_count)
 
 };
 
@@ -171,20 +183,17 @@ double host_log_score(uint64_t q1, uint64_t q2, uint64_t q3) {
 uint64_t cint_mask(int bytes) { return bytes >= 8 ? ~0ull : ((1ull << (8 * bytes)) - 1); }
 
 void free_all(qs_ctx* c) {
-    cudaFree(c->d_lca); cudaFree(c->d_idepth); cudaFree(c->d_PB);
+    cudaFree(c->d_lca); cudaFree(c->d_idepth);
+    cudaFree(c->d_run_off); cudaFree(c->d_run_end); cudaFree(c->d_run_pd); cudaFree(c->d_inner_parent); cudaFree(c->d_leaf_parent);
+    cudaFree(c->d_inner_node); cudaFree(c->d_node_parent); cudaFree(c->d_node_depth); cudaFree(c->d_node_edge); cudaFree(c->d_node_inner);
+    cudaFree(c->d_edge); cudaFree(c->d_edge_out); cudaFree(c->d_scan_scratch); cudaFree(c->d_scan_counter);
     cudaFree(c->d_off); cudaFree(c->d_parent); cudaFree(c->d_leaf);
     cudaFree(c->d_D); cudaFree(c->d_flags); cudaFree(c->d_table);
     cudaFree(c->d_class); cudaFree(c->d_order); cudaFree(c->d_nA); cudaFree(c->d_counter);
     cudaFree(c->d_tasks); cudaFree(c->d_enum);
-    cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best); cudaFree(c->d_pair_hint);
+    cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best); cudaFree(c->d_pair_score); cudaFree(c->d_pair_score_local);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
-}
-
-template <typename CINT>
-void launch_score(qs_ctx* c, const ScoreArgs& a) {
-    qs_score_table_kernel<CINT><<<(unsigned)c->score_blocks, 128, (size_t)c->n * sizeof(uint32_t), c->stream>>>(a);
-    c->launches++;
 }
 
 int run_distances(qs_ctx* c) {
@@ -520,14 +529,23 @@ int build_reference(qs_ctx* c, int n_nodes, const int32_t* parent, const int32_t
     // genesis is_bifurcating: max rank (links - 1) == 2 (genesis tree/function/functions.cpp:57-69)
     int max_rank = 0; bool all3 = true;
     R.inner_index.assign(n_nodes, -1);
-    for (int v = 0; v < n_nodes; ++v) {
-        int links = nchild[v] + (v != 0 ? 1 : 0);
-        max_rank = std::max(max_rank, links - 1);
-        if (nchild[v] > 0) {
-            R.inner_index[v] = (int)R.inner_node.size();
-            R.inner_node.push_back(v);
+    // inner index = rank of the node's first gap in the planar leaf order (gap g lies between leaves g and g+1 and belongs
+    // to lca(g, g+1); the first gap of v is the one after its first child).  Gaps of different nodes differ, so for leaves
+    // x < y the index of lca(x,y) is <= its first gap < y: the scan kernel's CTA of (c,d) only touches accumulator
+    // indices below c (kernels/score.cuh).  Nodes with a single child own no gap, are never an LCA and come last.
+    {
+        std::vector<std::pair<int, int>> order;                       // (first gap, node)
+        int unary = 0;
+        for (int v = 0; v < n_nodes; ++v) {
+            const int links = nchild[v] + (v != 0 ? 1 : 0);
+            max_rank = std::max(max_rank, links - 1);
+            if (nchild[v] == 0) continue;
             if (links != 3) all3 = false;
+            if (nchild[v] >= 2) order.emplace_back(hi[first_child[v]] - 1, v);
+            else order.emplace_back(n + (unary++), v);
         }
+        std::sort(order.begin(), order.end());
+        for (auto& o : order) { R.inner_index[o.second] = (int)R.inner_node.size(); R.inner_node.push_back(o.second); }
     }
     R.n_inner = (int)R.inner_node.size();
     R.bifurcating = (max_rank == 2);
@@ -545,74 +563,110 @@ int build_reference(qs_ctx* c, int n_nodes, const int32_t* parent, const int32_t
                 for (int x = lo[c1]; x < hi[c1]; ++x)
                     for (int y = lo[c2]; y < hi[c2]; ++y) { R.lca[(size_t)x * n + y] = iv; R.lca[(size_t)y * n + x] = iv; }
     }
-    return QS_OK;
-}
-
-// per-b block prefix of the table scan (kernels/score.cuh): thread = (c,d) pair, d in [dB, dE)
-int build_score_blocks(qs_ctx* c, int dB, int dE) {
-    if (c->score_dB == dB && c->score_dE == dE && c->d_PB) return QS_OK;
-    const int n = c->n;
-    std::vector<int64_t> PB(n + 1, 0);
-    int64_t acc = 0;
+    // rows of the LCA matrix, run-length encoded: for b, the runs of constant lca(a,b) over a = 0 .. b-1 (they follow the
+    // ancestors of b from the root down, so there are at most depth(b) of them)
+    R.run_off.assign(n + 1, 0); R.run_end.clear(); R.run_pd.clear();
     for (int b = 0; b < n; ++b) {
-        PB[b] = acc;
-        if (b >= 1 && b <= n - 3) {
-            int dlo = std::max(b + 2, dB);
-            if (dlo < dE) {
-                int64_t k0 = dlo - b - 1, k1 = dE - b - 1;       // pairs = sum_{k=k0}^{k1-1} k
-                int64_t pairs = k1 * (k1 - 1) / 2 - k0 * (k0 - 1) / 2;
-                acc += (pairs + 127) / 128;
-            }
+        R.run_off[b] = (uint32_t)R.run_end.size();
+        for (int x = 0; x < b;) {
+            const uint16_t pnode = R.lca[(size_t)b * n + x];
+            int y = x + 1;
+            while (y < b && R.lca[(size_t)b * n + y] == pnode) ++y;
+            R.run_end.push_back((uint32_t)y);
+            R.run_pd.push_back((uint32_t)pnode | ((uint32_t)R.idepth[pnode] << 16));
+            x = y;
         }
     }
-    PB[n] = acc;
-    c->score_blocks = acc;
-    if (acc > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "score grid too large");
-    int r;
-    if (!c->d_PB && (r = dev_alloc(c, &c->d_PB, n + 1))) return r;
-    QS_CUDA(c, cudaStreamSynchronize(c->stream));
-    QS_CUDA(c, cudaMemcpy(c->d_PB, PB.data(), (n + 1) * 8, cudaMemcpyHostToDevice));
-    c->score_dB = dB; c->score_dE = dE;
+    R.run_off[n] = (uint32_t)R.run_end.size();
+    R.inner_parent.assign(R.n_inner, -1);
+    for (int i = 0; i < R.n_inner; ++i) { const int v = R.inner_node[i]; if (v != 0) R.inner_parent[i] = R.inner_index[parent[v]]; }
+    R.leaf_parent.assign(n, -1);
+    for (int x = 0; x < n; ++x) R.leaf_parent[x] = R.inner_index[parent[R.leaf_node[x]]];
     return QS_OK;
 }
 
 int ensure_pair_arrays(qs_ctx* c) {
-    const size_t I = c->ref.n_inner;
+    const size_t I = c->ref.n_inner, E = (size_t)c->ref.n_nodes - 1;
     int r;
     if (!c->d_pair_sums && (r = dev_alloc(c, &c->d_pair_sums, I * I * 3))) return r;
     if (!c->d_pair_best && (r = dev_alloc(c, &c->d_pair_best, I * I))) return r;
-    if (!c->d_pair_hint && (r = dev_alloc(c, &c->d_pair_hint, I * I))) return r;
+    if (!c->d_pair_score && (r = dev_alloc(c, &c->d_pair_score, I * I))) return r;
+    if (!c->d_edge && (r = dev_alloc(c, &c->d_edge, 4 * E))) return r;
+    if (!c->d_edge_out && (r = dev_alloc(c, &c->d_edge_out, 7 * E))) return r;
+    if (!c->d_scan_counter && (r = dev_alloc(c, &c->d_scan_counter, 1))) return r;
+    return QS_OK;
+}
+
+int fill_i64(qs_ctx* c, long long* p, size_t count, long long v) {
+    qs_fill_i64_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((count + 255) / 256, 4096)), 256, 0, c->stream>>>(p, count, v);
+    c->launches++;
+    QS_CUDA(c, cudaGetLastError());
     return QS_OK;
 }
 
 int clear_pair_arrays(qs_ctx* c) {
     const size_t I = c->ref.n_inner;
     QS_CUDA(c, cudaMemsetAsync(c->d_pair_sums, 0, I * I * 3 * 8, c->stream));
-    QS_CUDA(c, cudaMemsetAsync(c->d_pair_best, 0xFF, I * I * 8, c->stream));
-    qs_fill_int_kernel<<<(unsigned)std::min<size_t>((I * I + 255) / 256, 4096), 256, 0, c->stream>>>(c->d_pair_hint, I * I, QS_HINT_NONE);
+    int r;
+    if ((r = fill_i64(c, c->d_pair_best, I * I, QS_I64_NONE))) return r;
+    return fill_i64(c, c->d_pair_score, I * I, QS_I64_NONE);
+}
+
+// CTA shape of the scan: a CTA owns one (c,d) and its threads the row pairs (b, c-1-b), so 256 threads cover c <= 512 in one
+// pass; 512 threads for wider references.  The per-CTA accumulators live in shared memory while they fit beside the rings.
+template <typename CINT, int THREADS>
+int launch_scan_t(qs_ctx* c, ScoreArgs& a) {
+    const size_t ring = scan_ring_bytes(THREADS), acc = scan_acc_bytes(c->n);
+    bool smem_acc = ring + acc + 1024 <= (size_t)c->smem_optin;
+    if (getenv("QS_SCAN_GLOBAL_ACC")) smem_acc = false;                                   // test hook: the large-n path on a small input
+    const size_t smem = ring + (smem_acc ? acc : 0);
+    int per_sm = std::max(1, std::min(2048 / THREADS, (int)((size_t)c->smem_optin / (smem + 1024))));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(a.n_items, (long long)c->num_sms * per_sm));
+    if (!smem_acc) {
+        const size_t need = (size_t)grid * acc;
+        if (need > c->scan_scratch_bytes) {
+            int r = dev_alloc(c, &c->d_scan_scratch, need / 8 + 1);
+            if (r) { c->scan_scratch_bytes = 0; return r; }
+            c->scan_scratch_bytes = need;
+        }
+        a.scratch = c->d_scan_scratch;
+    }
+    QS_CUDA(c, cudaMemsetAsync(c->d_scan_counter, 0, sizeof(int), c->stream));
+    if (smem_acc) {
+        QS_CUDA(c, cudaFuncSetAttribute(qs_scan_rows_kernel<CINT, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        qs_scan_rows_kernel<CINT, THREADS, true><<<grid, THREADS, smem, c->stream>>>(a);
+    } else {
+        QS_CUDA(c, cudaFuncSetAttribute(qs_scan_rows_kernel<CINT, THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        qs_scan_rows_kernel<CINT, THREADS, false><<<grid, THREADS, smem, c->stream>>>(a);
+    }
     c->launches++;
     QS_CUDA(c, cudaGetLastError());
     return QS_OK;
 }
 
+template <typename CINT>
+int launch_scan(qs_ctx* c, ScoreArgs& a) {
+    return c->n <= 1024 ? launch_scan_t<CINT, 256>(c, a) : launch_scan_t<CINT, 512>(c, a);
+}
+
 // scan a table holding the quartets with d in [dB, dE) and accumulate into the per-pair partials on the device
 int scan_table(qs_ctx* c, const void* table, int dB, int dE, int count_scale) {
-    int r;
-    if ((r = build_score_blocks(c, dB, dE))) return r;
-    if (c->score_blocks == 0) return QS_OK;
-    ScoreArgs a;
+    ScoreArgs a{};
+    a.n_items = scan_item_count(dB, dE);
+    if (a.n_items == 0) return QS_OK;
+    if (a.n_items > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "scan work-item count overflow");
     a.table = table; a.rank_base = binom4((uint64_t)dB); a.lca = c->d_lca; a.idepth = c->d_idepth;
-    a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.pair_hint = c->d_pair_hint; a.PB = c->d_PB; a.n = c->n; a.I = c->ref.n_inner;
+    a.run_off = c->d_run_off; a.run_end = c->d_run_end; a.run_pd = c->d_run_pd; a.inner_parent = c->d_inner_parent; a.leaf_parent = c->d_leaf_parent;
+    a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.pair_score = c->d_pair_score; a.scratch = nullptr; a.work_counter = c->d_scan_counter;
+    a.n = c->n; a.I = c->ref.n_inner;
     a.d_begin = dB; a.d_end = dE; a.count_scale = count_scale; a.cint_mask = cint_mask(c->cint_bytes);
     a.bifurcating = c->ref.bifurcating ? 1 : 0;
     switch (c->cint_bytes) {
-        case 1: launch_score<uint8_t>(c, a); break;
-        case 2: launch_score<uint16_t>(c, a); break;
-        case 4: launch_score<uint32_t>(c, a); break;
-        default: launch_score<unsigned long long>(c, a); break;
+        case 1: return launch_scan<uint8_t>(c, a);
+        case 2: return launch_scan<uint16_t>(c, a);
+        case 4: return launch_scan<uint32_t>(c, a);
+        default: return launch_scan<unsigned long long>(c, a);
     }
-    QS_CUDA(c, cudaGetLastError());
-    return QS_OK;
 }
 
 // QS_MODE_TABLE_FREE (the -s analogue): the shard's d-range is processed in slabs that fit the device; each slab is
@@ -656,7 +710,7 @@ int run_table_free(qs_ctx* c) {
         const size_t need = (size_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB)) * eb;
         if (need > c->table_bytes) {
             if (c->d_table) { cudaFree(c->d_table); c->d_table = nullptr; c->table_bytes = 0; }
-            cudaError_t e = cudaMalloc(&c->d_table, need);
+            cudaError_t e = cudaMalloc(&c->d_table, need + kTableSlack);
             if (e != cudaSuccess) {
                 cudaGetLastError();
                 char b_[256];
@@ -674,33 +728,74 @@ int run_table_free(qs_ctx* c) {
     return QS_OK;
 }
 
-// QS_MODE_TABLE: scan the resident table; both modes: per-pair partials -> host
+// QS_MODE_TABLE: scan the resident table into the device partials; QS_MODE_TABLE_FREE: qs_count has already done it.
+// Asynchronous: nothing is copied to the host and the stream is not drained.
 int run_score_scan(qs_ctx* c, int count_scale) {
     if (!c->has_ref) QS_FAIL(c, QS_E_STATE, "qs_set_reference has not been called");
     if (!c->counted) QS_FAIL(c, QS_E_STATE, "qs_count has not been called");
     if (count_scale != 1 && count_scale != 2) QS_FAIL(c, QS_E_ARG, "count_scale must be 1 or 2");
-    const size_t I = c->ref.n_inner;
+    if ((uint64_t)c->m * (uint64_t)count_scale >= (1ull << QS_TRIPLE_BITS) && c->cint_bytes >= 4)
+        QS_FAIL(c, QS_E_UNSUPPORTED, "%lld trees x count_scale %d: the LQ-IC selection packs counts into %d bits (fewer than %llu trees)", (long long)c->m, count_scale,
+                QS_TRIPLE_BITS, (1ull << QS_TRIPLE_BITS) / (unsigned)count_scale);
     int r;
+    c->partials_ready = false;
     if (c->mode == QS_MODE_TABLE_FREE) {
         if (!c->fused_partials_valid || c->fused_scale != count_scale)
             QS_FAIL(c, QS_E_STATE, "table-free context: partials were accumulated by qs_count with count_scale=%d", c->fused_scale);
     } else {
         if ((r = ensure_pair_arrays(c))) return r;
-        if ((r = build_score_blocks(c, c->d_begin, c->d_end))) return r;
         QS_CUDA(c, cudaEventRecord(c->ev[4], c->stream));
         if ((r = clear_pair_arrays(c))) return r;
         if ((r = scan_table(c, c->d_table, c->d_begin, c->d_end, count_scale))) return r;
         QS_CUDA(c, cudaEventRecord(c->ev[5], c->stream));
+        c->score_timed = true;
     }
-    c->h_pair_sums.resize(I * I * 3);
-    c->h_pair_best.resize(I * I);
-    QS_CUDA(c, cudaMemcpyAsync(c->h_pair_sums.data(), c->d_pair_sums, I * I * 3 * 8, cudaMemcpyDeviceToHost, c->stream));
-    QS_CUDA(c, cudaMemcpyAsync(c->h_pair_best.data(), c->d_pair_best, I * I * 8, cudaMemcpyDeviceToHost, c->stream));
+    c->partials_ready = true;
+    return QS_OK;
+}
+
+// per-edge reduction of the (possibly all-reduced) device partials + host evaluation of the selected triples / sums with the
+// host's libm in the reference's operation order.  Any of the outputs may be null.
+int run_edge_reduce(qs_ctx* c, int exact_qp, double* lqic, double* qpic, double* eqpic) {
+    if (!c->partials_ready) QS_FAIL(c, QS_E_STATE, "no scanned partials: call qs_score_scan (or qs_score) first");
+    const HostRef& R = c->ref;
+    const int E = R.n_nodes - 1, I = R.n_inner;
+    int r;
+    if ((r = fill_i64(c, c->d_edge, (size_t)4 * E, QS_I64_NONE))) return r;
+    EdgeArgs a{};
+    a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.pair_score = c->d_pair_score;
+    a.inner_node = c->d_inner_node; a.node_parent = c->d_node_parent; a.node_depth = c->d_node_depth; a.node_edge = c->d_node_edge; a.node_inner = c->d_node_inner;
+    a.edge_lq = c->d_edge; a.edge_eqp = c->d_edge + E; a.edge_lq_arg = c->d_edge + 2 * (size_t)E; a.edge_eqp_arg = c->d_edge + 3 * (size_t)E;
+    a.out = c->d_edge_out; a.I = I; a.E = E; a.n_nodes = R.n_nodes; a.bifurcating = R.bifurcating ? 1 : 0; a.exact_qp = exact_qp;
+    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>(((size_t)I * I + 255) / 256, (size_t)c->num_sms * 8));
+    qs_edge_reduce_kernel<1><<<blocks, 256, 0, c->stream>>>(a);
+    qs_edge_reduce_kernel<2><<<blocks, 256, 0, c->stream>>>(a);
+    qs_edge_gather_kernel<<<(unsigned)((R.n_nodes + 255) / 256), 256, 0, c->stream>>>(a);
+    c->launches += 3;
+    QS_CUDA(c, cudaGetLastError());
+    c->h_edge_out.resize((size_t)E * 7);
+    QS_CUDA(c, cudaMemcpyAsync(c->h_edge_out.data(), c->d_edge_out, (size_t)E * 7 * 8, cudaMemcpyDeviceToHost, c->stream));
     QS_CUDA(c, cudaStreamSynchronize(c->stream));
-    if (c->mode != QS_MODE_TABLE_FREE) {
+    if (c->score_timed) {
         float ms = 0;
         cudaEventElapsedTime(&ms, c->ev[4], c->ev[5]);
         c->score_ms = ms;
+        c->score_timed = false;
+    }
+    const double inf = std::numeric_limits<double>::infinity();
+    const uint64_t M = (1ull << QS_TRIPLE_BITS) - 1;
+    for (int e = 0; e < E; ++e) {
+        const unsigned long long* o = c->h_edge_out.data() + (size_t)e * 7;
+        if (lqic) lqic[e] = o[0] == QS_TRIPLE_NONE ? inf : host_log_score(o[0] >> (2 * QS_TRIPLE_BITS), (o[0] >> QS_TRIPLE_BITS) & M, o[0] & M);
+        for (int k = 0; k < 2; ++k) {
+            double* out = k == 0 ? eqpic : qpic;
+            if (!out) continue;
+            const unsigned long long* p = o + 1 + 3 * k;
+            if (!R.bifurcating || (p[0] == ~0ull && p[1] == ~0ull && p[2] == ~0ull)) { out[e] = inf; continue; }
+            uint64_t p1 = p[0], p2 = p[1], p3 = p[2];
+            if (!exact_qp) { p1 &= 0xffffffffull; p2 &= 0xffffffffull; p3 &= 0xffffffffull; }   // `unsigned p1,p2,p3` (QuartetScoreComputer.hpp:382)
+            out[e] = host_log_score(p1, p2, p3);
+        }
     }
     return QS_OK;
 }
@@ -793,23 +888,6 @@ void for_pair_rows_parallel(int I, int E, int n_arrays, double* const* out, F bo
             out[k][e] = m;
         }
     }
-}
-
-// LQ-IC partial of this shard: exact (host libm) QIC of each pair's selected quartet, min over path edges
-void lqic_from_pairs(const qs_ctx* c, double* lqic) {
-    const HostRef& R = c->ref;
-    const int I = R.n_inner, E = R.n_nodes - 1;
-    const uint64_t M = (1ull << QS_TRIPLE_BITS) - 1;
-    double* out[1] = {lqic};
-    for_pair_rows_parallel(I, E, 1, out, [&](int iu, double* const* mine) {
-        double* lq = mine[0];
-        for (int iv = iu + 1; iv < I; ++iv) {
-            const unsigned long long t = c->h_pair_best[(size_t)iu * I + iv];
-            if (t == QS_TRIPLE_NONE) continue;
-            const double qic = host_log_score(t >> (2 * QS_TRIPLE_BITS), (t >> QS_TRIPLE_BITS) & M, t & M);
-            for_path_edges(R, R.inner_node[iu], R.inner_node[iv], [&](int e) { if (qic < lq[e]) lq[e] = qic; });
-        }
-    });
 }
 
 // QP-IC / EQP-IC from (reduced) pair sums: QuartetScoreComputer.hpp:472-489
@@ -939,11 +1017,23 @@ int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int3
     if ((r = dev_alloc(ctx, &ctx->d_idepth, (size_t)ctx->ref.n_inner))) return r;
     QS_CUDA(ctx, cudaMemcpy(ctx->d_lca, ctx->ref.lca.data(), n * n * 2, cudaMemcpyHostToDevice));
     QS_CUDA(ctx, cudaMemcpy(ctx->d_idepth, ctx->ref.idepth.data(), (size_t)ctx->ref.n_inner * 2, cudaMemcpyHostToDevice));
-    if (ctx->d_pair_sums) { cudaFree(ctx->d_pair_sums); ctx->d_pair_sums = nullptr; }
-    if (ctx->d_pair_best) { cudaFree(ctx->d_pair_best); ctx->d_pair_best = nullptr; }
-    if (ctx->d_pair_hint) { cudaFree(ctx->d_pair_hint); ctx->d_pair_hint = nullptr; }
-    ctx->score_dB = ctx->score_dE = -1;
-    ctx->fused_partials_valid = false;
+    {   // run-length encoded LCA rows and the parent arrays of the scan / per-edge reduction kernels (kernels/score.cuh)
+        const HostRef& R = ctx->ref;
+        auto up = [&](auto** dst, const auto& v) -> int {
+            int rr = dev_alloc(ctx, dst, std::max<size_t>(1, v.size()));
+            if (rr) return rr;
+            if (!v.empty() && cudaMemcpy(*dst, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice) != cudaSuccess) { ctx->err = "cudaMemcpy of the reference arrays failed"; return QS_E_CUDA; }
+            return QS_OK;
+        };
+        if ((r = up(&ctx->d_run_off, R.run_off)) || (r = up(&ctx->d_run_end, R.run_end)) || (r = up(&ctx->d_run_pd, R.run_pd)) ||
+            (r = up(&ctx->d_inner_parent, R.inner_parent)) || (r = up(&ctx->d_leaf_parent, R.leaf_parent)) || (r = up(&ctx->d_inner_node, R.inner_node)) ||
+            (r = up(&ctx->d_node_parent, R.parent)) || (r = up(&ctx->d_node_depth, R.depth)) || (r = up(&ctx->d_node_edge, R.parent_edge)) ||
+            (r = up(&ctx->d_node_inner, R.inner_index)))
+            return r;
+    }
+    for (auto** q : {(void**)&ctx->d_pair_sums, (void**)&ctx->d_pair_best, (void**)&ctx->d_pair_score, (void**)&ctx->d_pair_score_local, (void**)&ctx->d_edge, (void**)&ctx->d_edge_out})
+        if (*q) { cudaFree(*q); *q = nullptr; }
+    ctx->fused_partials_valid = false; ctx->partials_ready = false;
     ctx->has_ref = true;
     return QS_OK;
 }
@@ -1041,7 +1131,7 @@ int qs_count(qs_ctx* ctx) {
         const size_t need = (size_t)nq * 3 * ctx->cint_bytes;
         if (need > ctx->table_bytes) {
             if (ctx->d_table) { cudaFree(ctx->d_table); ctx->d_table = nullptr; ctx->table_bytes = 0; }
-            cudaError_t e = cudaMalloc(&ctx->d_table, need);
+            cudaError_t e = cudaMalloc(&ctx->d_table, need + kTableSlack);
             if (e != cudaSuccess) { cudaGetLastError(); QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! count table of %zu bytes does not fit this device (use QS_MODE_TABLE_FREE or more shards)", need); }
             ctx->table_bytes = need;
         }
@@ -1070,9 +1160,51 @@ int qs_score_partials(qs_ctx* ctx, int count_scale, double* lqic_partial, uint64
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
     int r = run_score_scan(ctx, count_scale);
     if (r) return r;
-    lqic_from_pairs(ctx, lqic_partial);
-    memcpy(pair_sums, ctx->h_pair_sums.data(), ctx->h_pair_sums.size() * 8);
+    const size_t I = ctx->ref.n_inner;
+    QS_CUDA(ctx, cudaMemcpyAsync(pair_sums, ctx->d_pair_sums, I * I * 3 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    return run_edge_reduce(ctx, 0, lqic_partial, nullptr, nullptr);      // (drains the stream: the copy above has landed)
+}
+
+int qs_score_scan(qs_ctx* ctx, int count_scale) {
+    if (!ctx) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int r = run_score_scan(ctx, count_scale);
+    if (r) return r;
+    // this shard's own scores, kept for qs_score_select_winners after the caller's MIN all-reduce of pair_score
+    const size_t I = ctx->ref.n_inner;
+    if (!ctx->d_pair_score_local && (r = dev_alloc(ctx, &ctx->d_pair_score_local, I * I))) return r;
+    QS_CUDA(ctx, cudaMemcpyAsync(ctx->d_pair_score_local, ctx->d_pair_score, I * I * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     return QS_OK;
+}
+
+int qs_score_device_partials(qs_ctx* ctx, void** pair_sums, void** pair_score, void** pair_best, int64_t* n_pairs) {
+    if (!ctx || !pair_sums || !pair_score || !pair_best || !n_pairs) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
+    if (!ctx->partials_ready) QS_FAIL(ctx, QS_E_STATE, "no scanned partials: call qs_score_scan first");
+    *pair_sums = ctx->d_pair_sums; *pair_score = ctx->d_pair_score; *pair_best = ctx->d_pair_best;
+    *n_pairs = (int64_t)ctx->ref.n_inner * ctx->ref.n_inner;
+    return QS_OK;
+}
+
+int qs_score_select_winners(qs_ctx* ctx) {
+    if (!ctx) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
+    if (!ctx->partials_ready || !ctx->d_pair_score_local) QS_FAIL(ctx, QS_E_STATE, "call qs_score_scan first");
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t I = ctx->ref.n_inner;
+    qs_select_winners_kernel<<<(unsigned)std::max<size_t>(1, std::min<size_t>((I * I + 255) / 256, 4096)), 256, 0, ctx->stream>>>(ctx->d_pair_score_local, ctx->d_pair_score,
+                                                                                                                                ctx->d_pair_best, I * I);
+    ctx->launches++;
+    QS_CUDA(ctx, cudaGetLastError());
+    return QS_OK;
+}
+
+int qs_score_finish(qs_ctx* ctx, int exact_qp, double* lqic, double* qpic, double* eqpic) {
+    if (!ctx || !lqic) return QS_E_ARG;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    return run_edge_reduce(ctx, exact_qp, lqic, qpic, eqpic);
 }
 
 int qs_score_finalize(qs_ctx* ctx, int exact_qp, const double* lqic_reduced, const uint64_t* pair_sums_reduced,
@@ -1091,9 +1223,7 @@ int qs_score(qs_ctx* ctx, int count_scale, int exact_qp, double* lqic, double* q
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
     int r = run_score_scan(ctx, count_scale);
     if (r) return r;
-    lqic_from_pairs(ctx, lqic);
-    qp_from_pairs(ctx, (const uint64_t*)ctx->h_pair_sums.data(), exact_qp, qpic, eqpic);
-    return QS_OK;
+    return run_edge_reduce(ctx, exact_qp, lqic, qpic, eqpic);
 }
 
 int qs_shard_bounds(int n_taxa, int shard_index, int shard_count, int* s3_begin, int* s3_end, uint64_t* rank_begin, uint64_t* rank_end) {
@@ -1266,7 +1396,7 @@ int qs_load_table(qs_ctx* ctx, const char* path) {
     const size_t total = (size_t)(ctx->rank_end - ctx->rank_begin) * 3 * ctx->cint_bytes;
     if (total > ctx->table_bytes) {
         if (ctx->d_table) { cudaFree(ctx->d_table); ctx->d_table = nullptr; ctx->table_bytes = 0; }
-        cudaError_t e = cudaMalloc(&ctx->d_table, total);
+        cudaError_t e = cudaMalloc(&ctx->d_table, total + kTableSlack);
         if (e != cudaSuccess) { cudaGetLastError(); fclose(fp); QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! count table of %zu bytes does not fit this device", total); }
         ctx->table_bytes = total;
     }

@@ -17,12 +17,16 @@ class RefPairs:
             if p >= 0:
                 lo[p], hi[p] = min(lo[p], lo[v]), max(hi[p], hi[v])
         self.lo, self.hi = lo, hi
-        self.inner = [v for v in range(N) if ref.leaf_lookup_id[v] < 0]      # inner index = position in node order (qscuda.cu build_reference)
-        self.iidx = {v: i for i, v in enumerate(self.inner)}
+        self.inner = [v for v in range(N) if ref.leaf_lookup_id[v] < 0]
         self.I = len(self.inner)
         self.kids = {v: [] for v in self.inner}
         for c in range(1, N):
             self.kids[ref.parent[c]].append(c)
+        for v in self.inner:
+            self.kids[v].sort(key=lambda c: lo[c])                         # planar (Newick) order
+        # inner index = rank of the node's first gap in the planar leaf order (qscuda.cu build_reference); single-child nodes last
+        key = {v: (hi[self.kids[v][0]] - 1 if len(self.kids[v]) >= 2 else n + v) for v in self.inner}
+        self.iidx = {v: i for i, v in enumerate(sorted(self.inner, key=lambda v: key[v]))}
         self.full = frozenset(range(n))
 
     def link_sets(self, x):

@@ -364,3 +364,88 @@ def test_raw_qic_file_thread_count_independent(threads, golden, tmp_path, monkey
         p = str(tmp_path / "raw.txt")
         ctx.write_raw_qic(ref.taxa, p)
         assert open(p).read() == g["rawqic"]
+
+
+# ---- round 2: scan kernel variants, device-resident multi-shard reduction, documented limits ---------------------------
+
+@pytest.mark.parametrize("name", ["s32x270_spr", "s16x300_missing_poly", "s20x40_multiref_missing", "c2_multifurcating_ref"])
+def test_scan_with_global_accumulators(name, golden, monkeypatch):
+    """the scan keeps its per-CTA accumulators in global memory when they do not fit shared memory (n > ~2,300): forced here"""
+    monkeypatch.setenv("QS_SCAN_GLOBAL_ACC", "1")
+    g = golden(name)
+    _, ref, flat = load_input(g)
+    with run_ctx(ref, flat) as ctx:
+        for suffix, scale in (("", 1), ("_s", 2)):
+            for got, key in zip(ctx.score(scale), ("lqic", "qpic", "eqpic")):
+                want = g[key + suffix]
+                assert np.array_equal(np.isinf(got), np.isinf(want)), key + suffix
+                fin = np.isfinite(want)
+                assert np.allclose(got[fin], want[fin], rtol=0, atol=1e-9), key + suffix
+
+
+@pytest.mark.parametrize("G", [2, 5])
+@pytest.mark.parametrize("mode_name", ["table", "table_free"])
+def test_device_resident_shard_reduction(G, mode_name, tiny_slabs):
+    """The N-GPU score path with the partials left on the device (qs_score_scan / qs_score_device_partials /
+    qs_score_select_winners / qs_score_finish): G shard contexts on ONE GPU, the three all-reduces replaced by the same
+    element-wise SUM / MIN / MIN over the shards' device buffers -> the 1-shard scores, bit for bit."""
+    import torch
+    from quartetscores_b200 import QS_MODE_TABLE, QS_MODE_TABLE_FREE
+    from quartetscores_b200.multi import _DeviceArray
+    s = SyntheticInput(34, 320, 43, k_max=10, p_missing=0.08, p_contract=0.05, want_newick=False)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    with run_ctx(ref, s.flat) as ctx:
+        want = ctx.score(1)
+    mode = QS_MODE_TABLE if mode_name == "table" else QS_MODE_TABLE_FREE
+    stream = torch.cuda.current_stream()
+    ctxs = []
+    for g in range(G):
+        c = Context(ref.n_taxa, 2, mode=mode, shard_index=g, shard_count=G)
+        c.set_stream(stream.cuda_stream)
+        c.set_reference(ref)
+        c.add_trees(s.flat)
+        c.count()
+        c.score_scan(1)
+        ctxs.append(c)
+    dev = torch.device("cuda", 0)
+    views = []
+    for c in ctxs:
+        ps, sc, be, npairs = c.score_device_partials()
+        views.append((torch.as_tensor(_DeviceArray(ps, 3 * npairs), device=dev), torch.as_tensor(_DeviceArray(sc, npairs), device=dev),
+                      torch.as_tensor(_DeviceArray(be, npairs), device=dev)))
+    sums = torch.stack([v[0] for v in views]).sum(0)
+    score = torch.stack([v[1] for v in views]).min(0).values
+    for v in views:                                   # "all-reduce" SUM and MIN in place
+        v[0].copy_(sums)
+        v[1].copy_(score)
+    for c in ctxs:
+        c.score_select_winners()
+    best = torch.stack([v[2] for v in views]).min(0).values
+    for v in views:
+        v[2].copy_(best)
+    for c in ctxs:                                    # every rank finishes on its own and must get the same result
+        got = c.score_finish()
+        for a, b in zip(got, want):
+            assert np.array_equal(a, b)
+        c.close()
+
+
+def test_lq_selection_count_limit_is_refused_not_wrapped():
+    """m * count_scale >= 2^21 does not fit the packed triple of the LQ-IC selection: QS_E_UNSUPPORTED instead of a silently wrong
+    LQ-IC (the reference's log_score takes size_t, QuartetScoreComputer.hpp:135).  2^20 copies of one 5-taxon tree, uint32 CINT."""
+    from quartetscores_b200 import QSError
+    ref = flatten_reference(parse_newick("((A,B),(C,D),E);"))
+    m = 1 << 20
+    par = np.array([-1, 0, 1, 1, 0, 4, 4, 0], np.int32)               # ((A,B),(C,D),E) in pre-order
+    leaf = np.array([-1, -1, 0, 1, -1, 2, 3, 4], np.int32)
+    off = np.arange(m + 1, dtype=np.int64) * 8
+    with Context(5, 4) as ctx:
+        ctx.set_reference(ref)
+        ctx.add_trees_raw(off, np.tile(par, m), np.tile(leaf, m))
+        ctx.count()
+        assert ctx.get_counts().tolist() == [[m, 0, 0], [m, 0, 0], [m, 0, 0], [0, 0, m], [0, 0, m]]      # ABCD ABCE ABDE ACDE BCDE
+        lq, qp, eqp = ctx.score(1)                                     # m * 1 < 2^21: fine, every quartet agrees with the reference tree
+        assert np.all(lq[np.isfinite(lq)] == 1.0) and np.all(qp[np.isfinite(qp)] == 1.0)
+        with pytest.raises(QSError) as e:
+            ctx.score(2)                                               # m * 2 = 2^21
+        assert e.value.code == -6
