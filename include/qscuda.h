@@ -45,7 +45,10 @@ enum {
 /* mode for qs_create */
 enum {
     QS_MODE_TABLE = 0,      /* keep the (sharded) count table resident: fast + qs_get_counts / qs_raw_qic possible */
-    QS_MODE_TABLE_FREE = 1  /* -s / savemem analogue: counts are scored as they are produced, no table */
+    QS_MODE_TABLE_FREE = 1, /* -s / savemem analogue: counts are scored as they are produced, no table */
+    QS_MODE_AUTO = 2        /* the reference constructor's memory policy (QuartetScoreComputer.hpp:724-745) applied to HBM: every
+                             * qs_count keeps the shard's table resident if it fits this device beside the distance matrices
+                             * and falls back to table-free otherwise, instead of failing with QS_E_MEMORY */
 };
 
 /* device for qs_create: a host-only context.  It makes no CUDA call and supports only the host-side pieces
@@ -120,6 +123,11 @@ int qs_score(qs_ctx* ctx, int count_scale, int exact_qp, double* lqic, double* q
  * quartets of the three topology counts of every inner-node pair) -> all-reduce SUM.
  * qs_score_finalize turns reduced partials into the three score vectors on the host. */
 int qs_score_num_pairs(const qs_ctx* ctx, int64_t* n_pairs);
+/* Layout of the per-pair arrays: n_pairs = I x I for the I inner nodes of the reference tree; the pair {u,v} of inner indices
+ * u < v lives at u * I + v (the other half is unused).  Inner indices follow the planar leaf order (an inner node is ranked by
+ * the gap between the last leaf of its first child and the next leaf; nodes with a single child come last):
+ * qs_score_inner_nodes writes the reference-tree node id of every inner index (node_of_inner may be NULL to query I only). */
+int qs_score_inner_nodes(const qs_ctx* ctx, int32_t* node_of_inner, int64_t capacity, int64_t* n_inner);
 int qs_score_partials(qs_ctx* ctx, int count_scale, double* lqic_partial, uint64_t* pair_sums);
 int qs_score_finalize(qs_ctx* ctx, int exact_qp, const double* lqic_reduced, const uint64_t* pair_sums_reduced,
                       double* lqic, double* qpic, double* eqpic);
@@ -144,7 +152,8 @@ int qs_score_finish(qs_ctx* ctx, int exact_qp, double* lqic, double* qpic, doubl
 
 /* Parity hook for QuartetCounterLookup::countQuartetOccurrences (QuartetCounterLookup.hpp:300-318):
  * canonical per-tree counts (1 per tree) of the entries [rank_begin, rank_end) in table layout, 3*cint_bytes
- * per rank, copied to the host buffer `out`.  Ranks outside this shard read as zero.  QS_MODE_TABLE only. */
+ * per rank, copied to the host buffer `out`.  Ranks outside this shard read as zero.  A table-free context keeps no
+ * table: it counts the slabs that cover the range again (slow, but the same numbers). */
 int qs_get_counts(qs_ctx* ctx, uint64_t rank_begin, uint64_t rank_end, void* out);
 /* Rank range [begin,end) owned by this shard. */
 int qs_shard_range(const qs_ctx* ctx, uint64_t* rank_begin, uint64_t* rank_end);
@@ -162,10 +171,14 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats);
 /* Parity hook for the distance kernel: tree t's matrix as n x n uint16 (0xFFFF = taxon missing). */
 int qs_get_distances(qs_ctx* ctx, int64_t tree, uint16_t* out);
 
-/* Replaces: printRawQICScores (QuartetScoreComputer.hpp:623-690).  Writes "(a,b|c,d): qic" lines in the
- * reference's order and formatting; taxon_names[id] is the label of lookup id `id`.  QS_MODE_TABLE,
- * single shard only. */
+/* Replaces: printRawQICScores (QuartetScoreComputer.hpp:623-690), which the reference runs with either table type
+ * (src/QuartetScores.cpp:120-122).  Writes "(a,b|c,d): qic" lines in the reference's order and formatting; taxon_names[id] is
+ * the label of lookup id `id`.  The file is ordered by (a,b,c,d), the table by rank, so the whole table (C(n,4) x 3 x
+ * cint_bytes) is gathered in host memory first; a table-free context counts its slabs again for that.
+ * qs_write_raw_qic: one context that owns the whole rank space.  qs_write_raw_qic_shards: the contexts of all shards (same
+ * process, shard 0 .. G-1 in order); the reference tree and the error message live in ctxs[0]. */
 int qs_write_raw_qic(qs_ctx* ctx, int count_scale, const char* const* taxon_names, const char* path);
+int qs_write_raw_qic_shards(qs_ctx* const* ctxs, int n_ctxs, int count_scale, const char* const* taxon_names, const char* path);
 
 /* ---- host ingest -------------------------------------------------------------------------
  * Replaces: the two serial genesis parses of the evaluation-tree file (src/QuartetScores.cpp:23-32

@@ -7,13 +7,15 @@
 // depends on that numbering); the evaluation trees go through libqscuda's parallel single-pass parser.  All counting and scoring happens
 // in libqscuda.so; there is no CPU fallback (a missing GPU is a std::runtime_error).
 //
-// Multi-GPU: one process, one context per visible device (or $QS_NUM_GPUS), each owning a shard of the quartet
+// Multi-GPU: one process, one context per device ($QS_NUM_GPUS, default 1; or the ordinals in $QS_DEVICES), each owning a shard of the quartet
 // rank space and driven by its own host thread; the per-shard partials are reduced on the host (min for
 // LQ-IC, sum for the pair sums) — no collective is needed inside a single process.
 #pragma once
 
 #include "genesis/genesis.hpp"
 #include "qscuda.h"
+
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -119,16 +121,39 @@ QuartetScoreComputer<CINT>::QuartetScoreComputer(Tree const& refTree, const std:
     FlatTree ref;
     flatten_tree(refTree, ref, true, nullptr, &refNodeToId);
 
-    // the -s table of the reference stores doubled, CINT-wrapped counts; same scores otherwise
-    count_scale = savemem ? 2 : 1;
+    // The reference's memory policy (QuartetScoreComputer.hpp:724-745) decides two different things; both are kept.
+    //  (1) WHICH COUNTS ARE SCORED.  With -s, or when its n^4 table would exceed 0.9 x the host's RAM, the reference counts into
+    //      the memory-efficient table, whose entries are doubled and wrap in CINT — visible in QP-IC /
+    //      EQP-IC once the 32-bit accumulators wrap (App. B4).  The same test on the same host gives the same choice here
+    //      (count_scale 2), and the same stdout lines, so outputs match the reference binary run on this machine.
+    //  (2) WHERE THE TABLE LIVES.  Here that is a question of HBM, not host RAM: -s asks for no resident table
+    //      (QS_MODE_TABLE_FREE); otherwise QS_MODE_AUTO keeps each shard's table on its GPU if it fits and falls back to
+    //      table-free slabs if not — the reference's "Insufficient memory!" (:735-737) is only raised when even that fails.
+    const size_t nn = (size_t)n;
+    const size_t memoryLookupFast = nn * nn * nn * nn * sizeof(CINT);
+    const size_t memoryLookup = (nn * (nn - 1) * (nn - 2) * (nn - 3) / 24) * 3 * sizeof(CINT) + sizeof(size_t);
+    const size_t estimatedMemory = (size_t)sysconf(_SC_PHYS_PAGES) * (size_t)sysconf(_SC_PAGE_SIZE);       // getTotalSystemMemory (:610-621)
+    std::cout << "Estimated memory usages (in bytes):" << std::endl;
+    std::cout << "  Runtime-efficient Lookup table: " << memoryLookupFast << std::endl;
+    std::cout << "  Memory-efficient Lookup table: " << memoryLookup << std::endl;
+    std::cout << "  Estimated available memory: " << estimatedMemory << std::endl;
+    const bool compact = savemem || memoryLookupFast > 0.9 * estimatedMemory;
+    std::cout << (compact ? "Using memory-efficient Lookup table\n" : "Using runtime-efficient Lookup table\n");
+    count_scale = compact ? 2 : 1;
 
     // one context per GPU
     int n_gpus = 1;
     if (const char* env = std::getenv("QS_NUM_GPUS")) n_gpus = std::max(1, std::atoi(env));
-    const int mode = savemem ? QS_MODE_TABLE_FREE : QS_MODE_TABLE;
+    const int mode = savemem ? QS_MODE_TABLE_FREE : QS_MODE_AUTO;
+    // shard g runs on device g, or on the g-th entry of $QS_DEVICES (comma-separated ordinals; several shards may share a GPU)
+    std::vector<int> devices;
+    if (const char* env = std::getenv("QS_DEVICES")) {
+        for (const char* p = env; *p;) { devices.push_back(std::atoi(p)); while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+        if (!devices.empty()) n_gpus = (int)devices.size();
+    }
     ctxs.assign(n_gpus, nullptr);
     for (int g = 0; g < n_gpus; ++g) {
-        qs_check(nullptr, qs_create(&ctxs[g], n, (int)sizeof(CINT), mode, g, g, n_gpus), "qs_create");
+        qs_check(nullptr, qs_create(&ctxs[g], n, (int)sizeof(CINT), mode, devices.empty() ? g : devices[g], g, n_gpus), "qs_create");
         qs_check(ctxs[g], qs_set_count_scale(ctxs[g], count_scale), "qs_set_count_scale");
         qs_check(ctxs[g], qs_set_reference(ctxs[g], (int)refTree.node_count(), ref.parent.data(), ref.parent_edge.data(), ref.leaf_id.data(),
                                            ref.first_child.data(), ref.next_sibling.data()), "qs_set_reference");
@@ -206,10 +231,10 @@ QuartetScoreComputer<CINT>::QuartetScoreComputer(Tree const& refTree, const std:
 template<typename CINT>
 void QuartetScoreComputer<CINT>::printRawQICScores(Tree const& refTree, const std::string& rawFilePath) {
     (void)refTree;
-    if (ctxs.size() != 1) throw std::runtime_error("printRawQICScores needs the whole table on one GPU: run with QS_NUM_GPUS=1 and without -s");
     std::vector<const char*> names;
     for (auto const& t : taxa) names.push_back(t.c_str());
-    qs_check(ctxs[0], qs_write_raw_qic(ctxs[0], count_scale, names.data(), rawFilePath.c_str()), "qs_write_raw_qic");
+    // any table type and any number of shards, as the reference (QuartetScores.cpp:120-122 calls it regardless of -s)
+    qs_check(ctxs[0], qs_write_raw_qic_shards(ctxs.data(), (int)ctxs.size(), count_scale, names.data(), rawFilePath.c_str()), "qs_write_raw_qic_shards");
 }
 
 }  // namespace qsb200

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("QSCUDA_LIB") or os.path.join(_HERE, "libqscuda.so")  
 QS_OK = 0
 QS_MODE_TABLE = 0
 QS_MODE_TABLE_FREE = 1
+QS_MODE_AUTO = 2
 QS_DEVICE_NONE = -1
 
 _i32p = C.POINTER(C.c_int32)
@@ -38,6 +39,7 @@ SIGNATURES = {
     "qs_count": (C.c_int, [C.c_void_p]),
     "qs_score": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _f64p, _f64p, _f64p]),
     "qs_score_num_pairs": (C.c_int, [C.c_void_p, _i64p]),
+    "qs_score_inner_nodes": (C.c_int, [C.c_void_p, _i32p, C.c_int64, _i64p]),
     "qs_score_partials": (C.c_int, [C.c_void_p, C.c_int, _f64p, _u64p]),
     "qs_score_finalize": (C.c_int, [C.c_void_p, C.c_int, _f64p, _u64p, _f64p, _f64p, _f64p]),
     "qs_score_scan": (C.c_int, [C.c_void_p, C.c_int]),
@@ -50,6 +52,7 @@ SIGNATURES = {
     "qs_plan_stats": (C.c_int, [C.c_int, C.c_int, C.c_int, _i64p]),
     "qs_get_distances": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint16)]),
     "qs_write_raw_qic": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_char_p]),
+    "qs_write_raw_qic_shards": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.POINTER(C.c_char_p), C.c_char_p]),
     "qs_newick_flatten": (C.c_int, [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(C.c_char_p), C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_size_t]),
     "qs_flat_trees_view": (C.c_int, [C.c_void_p, _i64p, _i64p, C.POINTER(_i64p), C.POINTER(_i32p), C.POINTER(_i32p)]),
     "qs_flat_trees_free": (None, [C.c_void_p]),

@@ -135,6 +135,14 @@ class Context:
         self._check(self._lib.qs_score_num_pairs(self._h, C.byref(v)), "qs_score_num_pairs")
         return v.value
 
+    def inner_nodes(self) -> np.ndarray:
+        """reference-tree node id of every inner index (the order of the per-pair arrays, see include/qscuda.h)"""
+        n = C.c_int64()
+        self._check(self._lib.qs_score_inner_nodes(self._h, None, 0, C.byref(n)), "qs_score_inner_nodes")
+        out = np.empty(n.value, np.int32)
+        self._check(self._lib.qs_score_inner_nodes(self._h, _ptr(out, C.c_int32), n.value, C.byref(n)), "qs_score_inner_nodes")
+        return out
+
     def score_partials(self, count_scale: int = 1):
         lq = np.empty(self.edge_count, np.float64)
         sums = np.empty(self.num_pairs() * 3, np.uint64)
@@ -189,6 +197,14 @@ class Context:
     def write_raw_qic(self, taxa: Sequence[str], path: str, count_scale: int = 1):
         arr = (C.c_char_p * len(taxa))(*[t.encode() for t in taxa])
         self._check(self._lib.qs_write_raw_qic(self._h, count_scale, arr, path.encode()), "qs_write_raw_qic")
+
+    @staticmethod
+    def write_raw_qic_shards(ctxs, taxa: Sequence[str], path: str, count_scale: int = 1):
+        """-q file from the contexts of ALL shards (same process, shard 0 .. G-1): qs_write_raw_qic_shards."""
+        lib = ctxs[0]._lib
+        arr = (C.c_char_p * len(taxa))(*[t.encode() for t in taxa])
+        hs = (C.c_void_p * len(ctxs))(*[c._h for c in ctxs])
+        ctxs[0]._check(lib.qs_write_raw_qic_shards(hs, len(ctxs), count_scale, arr, path.encode()), "qs_write_raw_qic_shards")
 
     def last_timing(self):
         a, b, c = C.c_double(), C.c_double(), C.c_double()

@@ -16,27 +16,27 @@
 //   * the per-edge minima over paths are taken on the device too (qs_edge_*_kernel below); the host only evaluates
 //     log_score for the ~3 x edges selected triples / sums.
 //
-// qs_scan_rows_kernel (round 2; replaces the per-thread run scan of round 1, which read 48 bytes at a time from rows
-// ~270 KB apart and issued 0.4 global atomics per quartet — 5 % of the HBM roofline).  A CTA owns one (c,d): the
-// C(c,2) entries (b,a) of that pair are ONE contiguous piece of the table (rank = C(d,4)+C(c,3)+C(b,2)+a,
-// src/quartet_lookup_table.hpp:141-168).  A thread owns a row b (a = 0..b-1, contiguous) paired with the row c-1-b, so
-// all threads carry the same load, and the rows a warp reads at the same time are neighbours in memory.  The row is
-// streamed through a private shared-memory ring by 16-byte cp.async copies (four 48-byte groups = 8 entries each in
-// flight per thread, no register staging) and consumed 12 bytes (two entries) at a time.
-//   Along a row the pair key only changes where lca(a,b) changes: the host stores every row of the reference LCA matrix
-// run-length encoded (run_off/run_end/run_pd), so the key logic runs once per RUN, and the per-entry work is three
-// integer adds and an fp32 QIC estimate.  A run is flushed into CTA-level accumulators in shared memory, indexed by ONE
-// inner node because the other end of the key is implied by (c,d):
-//     key (x, r)           r = lca(c,d)                 -> accR[x]        x = p or q
-//     key (p, q)  p below q, q = lca(b,c) = the ancestor of p that joins c -> accP[p]  (q recorded beside it)
-//     key (q, p)  p above q, both ancestors of c deeper than r   -> accQ[depth(q)-dr-1][depth(p)-dr-1] (32 levels; deeper ones go
-//                                                                   straight to global memory)
-// Inner nodes are numbered by their first gap in the planar leaf order (qscuda.cu build_reference), so every index
-// touched by the CTA of (c,d) is < c and only c entries are zeroed and flushed.  One global atomic per touched key and CTA
-// instead of one per run: n^3 instead of ~0.4 C(n,4) atomics.
-//   LQ-IC selection without an fp64 log per quartet: a run keeps the minimum fp32 estimate (error < 5e-7); only if that
-// could beat the pair's current exact minimum (pair_score, with a conservative fp32 copy in shared memory) the run is
-// walked again by a cold function that evaluates the quartets within the error margin in fp64.
+// qs_scan_kernel (round 2; replaces the per-thread run scan of round 1, which read 48 bytes at a time from rows ~270 KB
+// apart, spent ~290 lane-instructions per quartet and issued 0.4 global atomics per quartet — 5 % of the HBM roofline).
+//   * A CTA owns one (c,d): the C(c,2) entries (b,a) of that pair are ONE contiguous piece of the table (rank =
+//     C(d,4)+C(c,3)+C(b,2)+a, src/quartet_lookup_table.hpp:141-168).  It is streamed through a shared-memory ring by TMA
+//     bulk copies (cp.async.bulk + full/empty mbarriers, 12-24 KB per stage), so control flow is uniform and every byte of the
+//     table is read exactly once.
+//   * The pair key (u,v) of a quartet has one end implied by (c,d), so the CTA accumulates in shared memory, indexed by ONE node:
+//       key (x, r)   r = lca(c,d)                                   -> accR[x]   x = lca(a,b) or lca(b,c)
+//       key (p, q)   p = lca(a,b) below q = lca(b,c)                -> accP[p]   (q is the ancestor of p that joins c)
+//       key (q, p)   p above q, both ancestors of c deeper than r   -> accQ[depth(q)-dr-1][depth(p)-dr-1]  (32 levels; deeper
+//                                                                      ones go straight to global memory)
+//     Inner nodes are numbered by their first gap in the planar leaf order (qscuda.cu build_reference), so every index the
+//     CTA of (c,d) touches is < c and only c entries are zeroed and flushed: one global atomic per touched key and CTA
+//     (~n^3 in total) instead of one per run of equal keys (~0.4 C(n,4)).
+//   * A thread takes 4 CONSECUTIVE entries of a staged chunk: their LCA / depth lookups are independent and overlap, and the
+//     sums go to shared memory as fire-and-forget 32-bit REDs (with a carry word only when the host cannot rule out an
+//     overflow inside one (c,d)).  (A MATCH.ANY + REDUX warp aggregation was measured first: 47 % of all instructions and
+//     the longest stalls, profiles/r02_c_scan_n500_ncu_full.txt.)
+//   * LQ-IC selection without an fp64 log per quartet: every quartet gets an fp32 estimate (error < 5e-7) that is compared
+//     with the slot's bound, an fp32 upper bound of the pair's current exact minimum (fetched from pair_score when the CTA
+//     starts, lowered as minima are found); only a quartet that may beat it is evaluated in fp64 (scan_candidate).
 #pragma once
 #include "common.cuh"
 #include <type_traits>
@@ -57,6 +57,7 @@ struct ScoreArgs {
     const uint32_t* run_pd;          //   inner index of lca(a,b) | its depth << 16
     const int32_t* inner_parent;     // [I] inner index of the parent inner node, -1 for the root
     const int32_t* leaf_parent;      // [n] inner index of the parent of leaf x
+    const int32_t* inner_gap;        // [I] first gap of the inner node = a leaf below its first child (n + k for single-child nodes)
     unsigned long long* pair_sums;   // [I*I][3]  key = min(u,v) * I + max(u,v)
     long long* pair_best;            // [I*I] packed triple of the min-QIC quartet, QS_I64_NONE = none
     long long* pair_score;           // [I*I] order-preserving int64 image of the EXACT (device fp64) score of pair_best
@@ -120,13 +121,17 @@ __device__ __noinline__ double dev_log_score(unsigned long long q1, unsigned lon
 // exact score is exactly 1.
 constexpr float QS_EST_EPS = 1e-6f;            // twice the estimate's error bound
 constexpr float QS_FILTER_MARGIN = 2e-6f;      // estimates this close to a run's minimum are evaluated exactly
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float dev_log_score_f32(unsigned q1, unsigned q2, unsigned q3) {
     const unsigned s = q1 + q2 + q3;
-    const float inv = __frcp_rn(fmaxf((float)s, 1.f)), il3 = 0.63092975357145743710f;      // 1/log2(3)
+    // MUFU.RCP / MUFU.LG2 without the denormal fix-ups of __frcp_rn / __log2f: the arguments are >= 1e-30 (rcp: 1 ulp, i.e. one
+    // more ~1e-7 on the estimate; still inside QS_EST_EPS, see tests/test_score_filter.py)
+    const float inv = rcp_approx(fmaxf((float)s, 1.f)), il3 = 0.63092975357145743710f;      // 1/log2(3)
     const float p1 = (float)q1 * inv, p2 = (float)q2 * inv, p3 = (float)q3 * inv;
-    float acc = p1 * __log2f(fmaxf(p1, 1e-30f));             // p = 0: 0 * log2(1e-30) = 0
-    acc = fmaf(p2, __log2f(fmaxf(p2, 1e-30f)), acc);
-    acc = fmaf(p3, __log2f(fmaxf(p3, 1e-30f)), acc);
+    float acc = p1 * lg2_approx(fmaxf(p1, 1e-30f));          // p = 0: 0 * log2(1e-30) = 0
+    acc = fmaf(p2, lg2_approx(fmaxf(p2, 1e-30f)), acc);
+    acc = fmaf(p3, lg2_approx(fmaxf(p3, 1e-30f)), acc);
     float qic = fmaf(acc, il3, 1.f);
     if (q1 < max(q2, q3)) qic = -qic;
     return s == 0 ? 0.f : qic;
@@ -143,45 +148,27 @@ __device__ __forceinline__ void ordered_triple(int rslot, int bifurcating, unsig
     else { q1 = c2; q2 = c0; q3 = c1; }
 }
 
-// ---- cold path: a run that may hold a new minimum of its pair ------------------------------------------------------
-// Walk the run again, evaluate in fp64 every quartet whose estimate is within the margin of the run's smallest one, and
-// publish the best if it beats the pair's exact minimum.  Protocol on (pair_score, pair_best): lower pair_score first
-// (atomicMin, strict), then install the triple with a CAS loop that gives up as soon as pair_score shows a better one —
-// at the end pair_score[key] is the minimum and pair_best[key] a triple that attains it.
-template <typename CINT>
-__device__ __noinline__ void scan_candidate_run(const CINT* __restrict__ row, int a0, int a1, int rslot, int bifurcating, int shift, unsigned long long mask,
-                                                float run_min, long long key, long long* pair_best, long long* pair_score, int* bound) {
+// ---- cold path: one quartet that may be the new minimum of its pair ---------------------------------------------------
+// Evaluate it in fp64 and publish it if it beats the pair's exact minimum.  Protocol on (pair_score, pair_best): lower
+// pair_score first (atomicMin, strict), then install the triple with a CAS loop that gives up as soon as pair_score shows a
+// better one — at the end pair_score[key] is the minimum and pair_best[key] a triple that attains it.  `bound` / `last_t` are
+// the CTA's shared-memory copies for the slot (a conservative fp32 bound of the minimum and the triple that set it): they only
+// filter, races on them are benign.
+__device__ __noinline__ void scan_candidate(unsigned long long q1, unsigned long long q2, unsigned long long q3, long long key, long long* pair_best,
+                                            long long* pair_score, int* bound, unsigned long long* last_t) {
+    const unsigned long long t = pack_triple(q1, q2, q3);
+    if (last_t && *reinterpret_cast<volatile unsigned long long*>(last_t) == t) return;      // the very counts that hold the slot's minimum
+    const long long mine = double_to_ordered(dev_log_score(q1, q2, q3));
     const long long cur = *reinterpret_cast<volatile long long*>(pair_score + key);
-    const double H = cur == QS_I64_NONE ? (double)INFINITY : ordered_to_double(cur);
-    if (bound && cur != QS_I64_NONE) atomicMin(bound, float_to_ordered(__double2float_ru(H)));
-    const float thr = run_min == 1.f ? run_min : run_min - QS_EST_EPS;
-    if (!((double)thr < H)) return;
-    double best_q = INFINITY;
-    unsigned long long best_t = QS_TRIPLE_NONE, last_t = QS_TRIPLE_NONE;
-    for (int x = a0; x < a1; ++x) {
-        const unsigned long long c0 = ((unsigned long long)row[(size_t)x * 3 + 0] << shift) & mask, c1 = ((unsigned long long)row[(size_t)x * 3 + 1] << shift) & mask,
-                                 c2 = ((unsigned long long)row[(size_t)x * 3 + 2] << shift) & mask;
-        unsigned long long q1, q2, q3;
-        ordered_triple(rslot, bifurcating, c0, c1, c2, q1, q2, q3);
-        const unsigned long long t = pack_triple(q1, q2, q3);
-        if (t == last_t) continue;
-        last_t = t;
-        if ((q1 | q2 | q3) < (1ull << 22)) {                     // (wider counts have no fp32 estimate: always exact)
-            const float est = dev_log_score_f32((unsigned)q1, (unsigned)q2, (unsigned)q3);
-            if (est > run_min + QS_FILTER_MARGIN) continue;
-        }
-        const double q = dev_log_score(q1, q2, q3);
-        if (q < best_q) { best_q = q; best_t = t; }
-    }
-    if (!(best_q < H)) return;
-    const long long mine = double_to_ordered(best_q);
+    if (bound) atomicMin(bound, float_to_ordered(__double2float_ru(ordered_to_double(min(cur, mine)))));
+    if (!(mine < cur)) return;
+    if (last_t) *reinterpret_cast<volatile unsigned long long*>(last_t) = t;
     if (atomicMin(pair_score + key, mine) <= mine) return;       // somebody holds an equal or better score
-    if (bound) atomicMin(bound, float_to_ordered(__double2float_ru(best_q)));
     unsigned long long* pb = reinterpret_cast<unsigned long long*>(pair_best + key);
     unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(pb);
     while (true) {
-        if (*reinterpret_cast<volatile long long*>(pair_score + key) < mine) return;     // a better one came in: its owner installs its triple
-        const unsigned long long prev = atomicCAS(pb, old, best_t);
+        if (*reinterpret_cast<volatile long long*>(pair_score + key) < mine) return;         // a better one came in: its owner installs its triple
+        const unsigned long long prev = atomicCAS(pb, old, t);
         if (prev == old) return;
         old = prev;
     }
@@ -190,20 +177,14 @@ __device__ __noinline__ void scan_candidate_run(const CINT* __restrict__ row, in
 // ---- accumulators of one CTA ------------------------------------------------------------------------------------------
 constexpr int QS_Q4_LEVELS = 32;                                 // accQ covers ancestors of c up to 32 levels below r
 constexpr int QS_Q4_SLOTS = QS_Q4_LEVELS * (QS_Q4_LEVELS - 1) / 2;
-constexpr int QS_SCAN_STAGES = 2;                                // 48-byte groups in flight per thread (96 bytes: ~70 KB per SM at 768 threads)
-constexpr int QS_SCAN_SLOT_BYTES = QS_SCAN_STAGES * 48 + 16;     // (+16: consecutive threads start 28 words apart -> 4-way instead of 16-way bank conflicts)
-// layout: sums [3][n_acc] u64 | bound [n_acc] int | pq [n] u16   with n_acc = 2 n + QS_Q4_SLOTS: accR [0,n), accP [n,2n), accQ [2n, 2n+496)
-__host__ __device__ __forceinline__ size_t scan_acc_bytes(int n) { return (size_t)(2 * n + QS_Q4_SLOTS) * 28 + (size_t)((n + 7) / 8 * 8) * 2 + 64; }
-__host__ __device__ __forceinline__ size_t scan_ring_bytes(int threads) { return (size_t)threads * QS_SCAN_SLOT_BYTES; }
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+constexpr int QS_SCAN_STEPS = 4;                                 // entries per thread and staged chunk
+__host__ __device__ constexpr int scan_stages(int threads) { return threads >= 1024 ? 2 : 3; }
+__host__ __device__ constexpr uint32_t scan_chunk_bytes(int threads) { return (uint32_t)threads * QS_SCAN_STEPS * 6u; }
+// accumulator slots: accR [0,n), accP [n,2n), accQ [2n, 2n+496).  Per slot: last_t u64 | lo[3] u32 | hi[3] u32 | bound int; then pq [n] u16
+__host__ __device__ __forceinline__ size_t scan_acc_bytes(int n) { return (size_t)(2 * n + QS_Q4_SLOTS) * 36 + (size_t)((n + 7) / 8 * 8) * 2 + 64; }
+__host__ __device__ __forceinline__ size_t scan_ring_bytes(int threads, int cint_bytes) {
+    return 128 + (cint_bytes == 2 ? (size_t)scan_stages(threads) * scan_chunk_bytes(threads) : 0);
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-enum { RUN_DEAD = 0, RUN_R = 1, RUN_P = 2, RUN_Q4 = 3, RUN_G = 4 };
 
 // work item -> (c, d): items are ordered by c descending (the largest pieces first), d ascending inside a c
 __host__ __device__ __forceinline__ long long scan_item_count(int dB, int dE) {
@@ -225,23 +206,48 @@ __device__ __forceinline__ void scan_item_decode(long long j, int dB, int dE, in
     }
 }
 
-template <typename CINT, int THREADS, bool SMEM_ACC>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) qs_scan_rows_kernel(const ScoreArgs a) {
-    extern __shared__ __align__(16) unsigned char sm_scan[];
+__device__ __forceinline__ int bound_from_score(long long sc) {
+    return sc == QS_I64_NONE ? QS_BOUND_NONE : float_to_ordered(__double2float_ru(ordered_to_double(sc)));
+}
+
+// CARRY: the 32-bit shared-memory sums may overflow inside one (c,d) (max count x C(c,2) >= 2^32, decided by the host):
+// every add then returns the old value and feeds a carry word.  Without it the adds are fire-and-forget REDs.
+template <typename CINT, int THREADS, bool SMEM_ACC, bool CARRY>
+__global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_kernel(const ScoreArgs a) {
+    extern __shared__ __align__(128) unsigned char sm_scan[];
     __shared__ int s_item;
     __shared__ int s_anc[QS_Q4_LEVELS];
+    constexpr bool RING = sizeof(CINT) == 2;
+    constexpr int K = QS_SCAN_STEPS, STAGES = scan_stages(THREADS), CHUNK = THREADS * K, WARPS = THREADS / 32;
+    constexpr uint32_t CHUNK_BYTES = scan_chunk_bytes(THREADS);
     const int tid = threadIdx.x, n = a.n;
     const int n_acc = 2 * n + QS_Q4_SLOTS;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sm_scan);            // [STAGES] chunk landed (TMA transaction barrier)
+    uint64_t* empty = full + 4;                                       // [STAGES] every warp is done with the chunk
+    unsigned char* ring = sm_scan + 128;
     // accumulators: shared memory, or (large n) this CTA's region of a.scratch
-    unsigned char* acc_base = SMEM_ACC ? sm_scan + scan_ring_bytes(THREADS) : reinterpret_cast<unsigned char*>(a.scratch) + (size_t)blockIdx.x * scan_acc_bytes(n);
-    unsigned long long* acc_s = reinterpret_cast<unsigned long long*>(acc_base);                 // [3][n_acc]
-    int* acc_b = reinterpret_cast<int*>(acc_base + (size_t)n_acc * 24);                           // [n_acc]
-    uint16_t* acc_pq = reinterpret_cast<uint16_t*>(acc_base + (size_t)n_acc * 28);                // [n]
-    unsigned char* ring = sm_scan + (size_t)tid * QS_SCAN_SLOT_BYTES;
+    unsigned char* acc_base = SMEM_ACC ? sm_scan + scan_ring_bytes(THREADS, (int)sizeof(CINT)) : reinterpret_cast<unsigned char*>(a.scratch) + (size_t)blockIdx.x * scan_acc_bytes(n);
+    unsigned long long* acc_t = reinterpret_cast<unsigned long long*>(acc_base);                  // [n_acc] triple that set the slot's bound
+    uint32_t* acc_lo = reinterpret_cast<uint32_t*>(acc_base + (size_t)n_acc * 8);                 // [3][n_acc] low words of the sums
+    uint32_t* acc_hi = acc_lo + 3 * (size_t)n_acc;                                                // [3][n_acc] carries
+    int* acc_b = reinterpret_cast<int*>(acc_hi + 3 * (size_t)n_acc);                              // [n_acc] fp32 bound of the key's minimum (ordered int)
+    uint16_t* acc_pq = reinterpret_cast<uint16_t*>(acc_b + n_acc);                                // [n] q of the accP key (p, q)
     const int shift = a.count_scale == 2 ? 1 : 0;
+    const uint32_t mask32 = (uint32_t)a.cint_mask;                    // (counts are <= m < 2^31 whatever CINT is; the scaled value is masked to CINT)
     const CINT* table = reinterpret_cast<const CINT*>(a.table);
+    const unsigned char* tbytes = reinterpret_cast<const unsigned char*>(a.table);
     const bool bif = a.bifurcating != 0;
-    typedef typename std::conditional<(sizeof(CINT) <= 2), uint32_t, unsigned long long>::type sum_t;
+    uint32_t full_phase = 0, empty_phase = 0;
+    if (RING && tid == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
+        fence_mbar_init();
+    }
+    auto pair_key = [&](int u, int v) -> long long { return (long long)min(u, v) * a.I + max(u, v); };
+    auto add_sum = [&](int k, int slot, uint32_t v) {
+        if (v == 0) return;
+        if (CARRY) { const uint32_t old = atomicAdd(acc_lo + k * n_acc + slot, v); if (old + v < old) atomicAdd(acc_hi + k * n_acc + slot, 1u); }
+        else atomicAdd(acc_lo + k * n_acc + slot, v);
+    };
 
     while (true) {
         __syncthreads();
@@ -252,172 +258,158 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 3 : 1)) qs_scan_row
         int c, d;
         scan_item_decode(item, a.d_begin, a.d_end, c, d);
         const int r = a.lca[(size_t)c * n + d], dr = a.idepth[r];
-        // zero what this (c,d) can touch: indices < c of accR / accP, all of accQ
-        for (int x = tid; x < c; x += THREADS) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) { acc_s[(size_t)k * n_acc + x] = 0; acc_s[(size_t)k * n_acc + n + x] = 0; }
-            acc_b[x] = QS_BOUND_NONE; acc_b[n + x] = QS_BOUND_NONE;
-        }
-        for (int x = tid; x < QS_Q4_SLOTS; x += THREADS) {
-#pragma unroll
-            for (int k = 0; k < 3; ++k) acc_s[(size_t)k * n_acc + 2 * n + x] = 0;
-            acc_b[2 * n + x] = QS_BOUND_NONE;
-        }
-        if (tid < QS_Q4_LEVELS) s_anc[tid] = -1;
-        __syncthreads();
-        if (tid == 0) {                                        // ancestors of leaf c at depths dr+1 .. dr+32
-            for (int x = a.leaf_parent[c]; x >= 0; x = a.inner_parent[x]) {
+        // the pair's entries (b,a), a < b < c: L = C(c,2) consecutive table entries from E0, read in 48-byte groups
+        const uint64_t E0 = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
+        const int L = c * (c - 1) / 2;
+        const uint64_t G0 = E0 >> 3, G1 = (E0 + (uint64_t)L + 7) >> 3;
+        const int n_chunks = (int)((G1 - G0 + CHUNK / 8 - 1) / (CHUNK / 8));
+        auto issue = [&](int k) {                                // thread 0: chunk k of this item -> its ring stage
+            const uint64_t g = G0 + (uint64_t)k * (CHUNK / 8);
+            const uint32_t bytes = (uint32_t)min((uint64_t)(CHUNK / 8), G1 - g) * 48u;
+            uint64_t* bar = &full[k % STAGES];
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s(ring + (size_t)(k % STAGES) * CHUNK_BYTES, tbytes + g * 48, bytes, bar);
+        };
+        if (tid == 0) {
+            if (RING) for (int k = 0; k < STAGES && k < n_chunks; ++k) issue(k);     // in flight while the accumulators are prepared
+            for (int x = 0; x < QS_Q4_LEVELS; ++x) s_anc[x] = -1;
+            for (int x = a.leaf_parent[c]; x >= 0; x = a.inner_parent[x]) {          // ancestors of leaf c at depths dr+1 .. dr+32
                 const int dx = a.idepth[x];
                 if (dx <= dr) break;
                 if (dx - dr - 1 < QS_Q4_LEVELS) s_anc[dx - dr - 1] = x;
             }
         }
-        const uint64_t cd_base = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;     // entry index of (a=0, b=0 .. ) of this pair
-
-        // ---- rows: thread k owns rows 1+k and c-1-k (together c entries) ----
-        for (int k = tid; 2 * k + 2 <= c; k += THREADS) {
-#pragma unroll 1
-            for (int half = 0; half < 2; ++half) {
-                const int b = half == 0 ? 1 + k : c - 1 - k;
-                if (half == 1 && b <= 1 + k) break;
-                const int q = a.lca[(size_t)b * n + c], dq = a.idepth[q];
-                const int mqr = min(dq, dr);
-                const uint64_t e_begin = cd_base + (uint64_t)b * (b - 1) / 2;
-                const CINT* row = table + e_begin * 3;
-                // per-run state
-                uint32_t ri = a.run_off[b];
-                int run_end_a = 0, run_start = 0, type = RUN_DEAD, idx = 0, rslot = 0, pnode = 0;
-                sum_t s0 = 0, s1 = 0, s2 = 0;       // per-run sums: <= 65535 x 32768 entries fit 32 bits for 1- and 2-byte counters
-                float mn = INFINITY;
-                auto flush_run = [&](int a_now) {
-                    if (type == RUN_DEAD) return;
-                    const sum_t q1 = rslot ? s2 : s0, q3 = rslot ? s0 : s2;
-                    int* bptr = nullptr;
-                    long long key;
-                    if (type == RUN_G) {
-                        key = (long long)min(q, pnode) * a.I + max(q, pnode);
-                        if (bif) {
-                            unsigned long long* ps = a.pair_sums + (size_t)key * 3;
-                            if (q1) atomicAdd(ps, (unsigned long long)q1);
-                            if (s1) atomicAdd(ps + 1, (unsigned long long)s1);
-                            if (q3) atomicAdd(ps + 2, (unsigned long long)q3);
-                        }
-                    } else {
-                        if (bif) {
-                            if (q1) atomicAdd(acc_s + idx, (unsigned long long)q1);
-                            if (s1) atomicAdd(acc_s + n_acc + idx, (unsigned long long)s1);
-                            if (q3) atomicAdd(acc_s + 2 * (size_t)n_acc + idx, (unsigned long long)q3);
-                        }
-                        bptr = acc_b + idx;
-                        if (type == RUN_P) acc_pq[idx - n] = (uint16_t)q;
-                    }
-                    const float bound = bptr ? ordered_to_float(*reinterpret_cast<volatile int*>(bptr)) : INFINITY;
-                    if ((mn == 1.f ? mn : mn - QS_EST_EPS) < bound) {
-                        if (type == RUN_R) key = (long long)min(idx, r) * a.I + max(idx, r);
-                        else if (type == RUN_P) key = (long long)min(idx - n, q) * a.I + max(idx - n, q);
-                        else key = (long long)min(q, pnode) * a.I + max(q, pnode);
-                        scan_candidate_run<CINT>(row, run_start, a_now, rslot, a.bifurcating, shift, a.cint_mask, mn, key, a.pair_best, a.pair_score, bptr);
-                    }
-                };
-                auto next_run = [&](int a_now) {
-                    flush_run(a_now);
-                    run_start = a_now;
-                    run_end_a = (int)a.run_end[ri];
-                    const uint32_t pd = a.run_pd[ri];
-                    ++ri;
-                    const int p = (int)(pd & 0xffffu), dp = (int)(pd >> 16);
-                    const int S0 = dp + dr, S2 = min(dp, mqr) + dq;
-                    s0 = s1 = s2 = 0; mn = INFINITY; pnode = p;
-                    if (S0 > S2) {                       // ab|cd: u = deeper(p,q), v = deeper(q,r)
-                        rslot = 0;
-                        if (dr > dq) { type = RUN_R; idx = dp > dq ? p : q; }
-                        else { type = RUN_P; idx = n + p; }            // (dp > dq here: u = p, v = q)
-                    } else if (S2 > S0) {                // ad|bc: u = q, v = deeper(p,r)
-                        rslot = 2;
-                        if (dp > dr) {
-                            const int i = dq - dr - 1, jj = dp - dr - 1;
-                            if (i < QS_Q4_LEVELS) { type = RUN_Q4; idx = 2 * n + i * (i - 1) / 2 + jj; }
-                            else type = RUN_G;
-                        } else { type = RUN_R; idx = q; }
-                    } else type = RUN_DEAD;
-                };
-                auto entry = [&](int x, uint32_t r0, uint32_t r1, uint32_t r2) {
-                    if (x == run_end_a) next_run(x);
-                    const uint32_t c0 = (uint32_t)(((unsigned long long)r0 << shift) & a.cint_mask), c1 = (uint32_t)(((unsigned long long)r1 << shift) & a.cint_mask),
-                                   c2 = (uint32_t)(((unsigned long long)r2 << shift) & a.cint_mask);
-                    s0 += c0; s1 += c1; s2 += c2;
-                    mn = fminf(mn, dev_log_score_f32(rslot ? c2 : c0, c1, rslot ? c0 : c2));
-                };
-                if (sizeof(CINT) == 2) {
-                    // 48-byte groups (8 entries) of the row, 16-byte aligned because the table is: group g = entries [8g, 8g+8)
-                    const unsigned char* tbytes = reinterpret_cast<const unsigned char*>(table);
-                    const long long g_first = (long long)(e_begin >> 3), g_last = (long long)((e_begin + b - 1) >> 3);
-                    auto issue = [&](long long g, uint32_t ring_off) {       // (an empty group is committed past the row's end: the group count stays uniform)
-                        if (g <= g_last) {
-                            const unsigned char* src = tbytes + (size_t)g * 48;
-                            unsigned char* dst = ring + ring_off;
-                            cp_async16(dst, src); cp_async16(dst + 16, src + 16); cp_async16(dst + 32, src + 32);
-                        }
-                        cp_async_commit();
-                    };
+        __syncthreads();
+        // zero what this (c,d) can touch (indices < c of accR / accP, all of accQ) and fetch the keys' current minima as fp32 bounds
+        for (int x = tid; x < c; x += THREADS) {
 #pragma unroll
-                    for (int s = 0; s < QS_SCAN_STAGES; ++s) issue(g_first + s, (uint32_t)s * 48u);
-                    const long long P_first = g_first * 4, P_begin = (long long)(e_begin >> 1), P_end = (long long)((e_begin + b - 1) >> 1);
-                    uint32_t off = 0;                                 // byte offset of the current pair inside the ring
-                    for (long long P = P_first; P <= P_end; ++P) {
-                        if ((P & 3) == 0) cp_async_wait<QS_SCAN_STAGES - 1>();
-                        if (P >= P_begin) {
-                            const uint32_t w0 = *reinterpret_cast<const uint32_t*>(ring + off), w1 = *reinterpret_cast<const uint32_t*>(ring + off + 4),
-                                           w2 = *reinterpret_cast<const uint32_t*>(ring + off + 8);
-                            const int x0 = (int)(2 * P - (long long)e_begin);
-                            if (x0 >= 0) entry(x0, w0 & 0xffffu, w0 >> 16, w1 & 0xffffu);
-                            if (x0 + 1 < b) entry(x0 + 1, w1 >> 16, w2 & 0xffffu, w2 >> 16);
-                        }
-                        off += 12;
-                        if ((P & 3) == 3) {                          // the group is consumed: refill its slot with the group QS_SCAN_STAGES ahead
-                            issue((P >> 2) + QS_SCAN_STAGES, off - 48u);
-                            if (off == QS_SCAN_STAGES * 48) off = 0;
-                        }
-                    }
-                    cp_async_wait<0>();
-                } else {
-                    for (int x = 0; x < b; ++x) entry(x, (uint32_t)row[(size_t)x * 3], (uint32_t)row[(size_t)x * 3 + 1], (uint32_t)row[(size_t)x * 3 + 2]);   // (counts <= m < 2^31)
+            for (int k = 0; k < 3; ++k) { acc_lo[k * n_acc + x] = 0; acc_lo[k * n_acc + n + x] = 0; if (CARRY) { acc_hi[k * n_acc + x] = 0; acc_hi[k * n_acc + n + x] = 0; } }
+            acc_t[x] = QS_TRIPLE_NONE; acc_t[n + x] = QS_TRIPLE_NONE;
+            acc_b[x] = x != r ? bound_from_score(a.pair_score[pair_key(x, r)]) : QS_BOUND_NONE;
+            int bp = QS_BOUND_NONE;
+            const int g = a.inner_gap[x];
+            if (g < c) { const int qq = a.lca[(size_t)g * n + c]; if (qq != x) bp = bound_from_score(a.pair_score[pair_key(x, qq)]); }
+            acc_b[n + x] = bp;
+        }
+        for (int x = tid; x < QS_Q4_SLOTS; x += THREADS) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) { acc_lo[k * n_acc + 2 * n + x] = 0; if (CARRY) acc_hi[k * n_acc + 2 * n + x] = 0; }
+            acc_t[2 * n + x] = QS_TRIPLE_NONE;
+            int i = (int)((1.f + sqrtf(1.f + 8.f * (float)x)) * 0.5f);
+            while (i * (i - 1) / 2 > x) --i;
+            while ((i + 1) * i / 2 <= x) ++i;
+            const int u = s_anc[i], v = s_anc[x - i * (i - 1) / 2];
+            acc_b[2 * n + x] = (u >= 0 && v >= 0) ? bound_from_score(a.pair_score[pair_key(u, v)]) : QS_BOUND_NONE;
+        }
+        __syncthreads();
+
+        for (int k = 0; k < n_chunks; ++k) {
+            const int stage = k % STAGES;
+            if (RING) { mbar_wait(&full[stage], (full_phase >> stage) & 1u); full_phase ^= 1u << stage; }
+            // this thread's K consecutive entries of the chunk: the loads of the K entries are independent and overlap
+            const int pos0 = tid * K;
+            const long long x0 = (long long)((G0 << 3) + (uint64_t)k * CHUNK + pos0) - (long long)E0;
+            int b = 1, aa = 0;
+            if (x0 + K > 0 && x0 < L) {                                                  // row of the first entry in range: C(b,2) <= x < C(b+1,2)
+                const int x = (int)max(x0, 0LL);
+                b = (int)((1.f + sqrtf(1.f + 8.f * (float)x)) * 0.5f);
+                while (b * (b - 1) / 2 > x) --b;
+                while ((b + 1) * b / 2 <= x) ++b;
+                aa = x - b * (b - 1) / 2;
+            }
+            int slot[K], rs[K], ku[K], kv[K], qn[K];
+            uint32_t c0[K], c1[K], c2[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                const long long xl = x0 + i;
+                slot[i] = -1; rs[i] = 0; ku[i] = kv[i] = qn[i] = 0; c0[i] = c1[i] = c2[i] = 0;
+                if (xl >= 0 && xl < L) {
+                    const int p = a.lca[(size_t)b * n + aa], q = a.lca[(size_t)b * n + c];
+                    const int dp = a.idepth[p], dq = a.idepth[q];
+                    uint32_t r0, r1, r2;
+                    if (RING) {
+                        const uint16_t* e = reinterpret_cast<const uint16_t*>(ring + (size_t)stage * CHUNK_BYTES) + (pos0 + i) * 3;
+                        r0 = e[0]; r1 = e[1]; r2 = e[2];
+                    } else { const CINT* e = table + (E0 + (uint64_t)xl) * 3; r0 = (uint32_t)e[0]; r1 = (uint32_t)e[1]; r2 = (uint32_t)e[2]; }
+                    c0[i] = (r0 << shift) & mask32; c1[i] = (r1 << shift) & mask32; c2[i] = (r2 << shift) & mask32;
+                    const int S0 = dp + dr, S2 = min(dp, min(dq, dr)) + dq;
+                    qn[i] = q;
+                    if (S0 > S2) {                       // ab|cd: u = deeper(p,q), v = deeper(q,r)
+                        if (dr > dq) { slot[i] = dp > dq ? p : q; ku[i] = slot[i]; kv[i] = r; }
+                        else { slot[i] = n + p; ku[i] = p; kv[i] = q; }        // (dp > dq here)
+                    } else if (S2 > S0) {                // ad|bc: u = q, v = deeper(p,r)
+                        rs[i] = 2;
+                        if (dp > dr) {
+                            const int lq = dq - dr - 1, lp = dp - dr - 1;
+                            slot[i] = lq < QS_Q4_LEVELS ? 2 * n + lq * (lq - 1) / 2 + lp : -2;     // -2: deeper than accQ reaches -> global memory
+                            ku[i] = q; kv[i] = p;
+                        } else { slot[i] = q; ku[i] = q; kv[i] = r; }
+                    }                                    // else: unresolved in the reference tree (:559-562), slot stays -1
+                    if (++aa == b) { aa = 0; ++b; }
                 }
-                flush_run(b);
+            }
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                if (slot[i] == -1) continue;
+                const uint32_t a1 = rs[i] ? c2[i] : c0[i], a3 = rs[i] ? c0[i] : c2[i];   // (reference topology, crossing, other)
+                if (bif) {
+                    if (slot[i] >= 0) {
+                        add_sum(0, slot[i], a1); add_sum(1, slot[i], c1[i]); add_sum(2, slot[i], a3);
+                        if (slot[i] >= n && slot[i] < 2 * n) acc_pq[slot[i] - n] = (uint16_t)qn[i];
+                    } else {
+                        unsigned long long* ps = a.pair_sums + (size_t)pair_key(ku[i], kv[i]) * 3;
+                        if (a1) atomicAdd(ps, (unsigned long long)a1);
+                        if (c1[i]) atomicAdd(ps + 1, (unsigned long long)c1[i]);
+                        if (a3) atomicAdd(ps + 2, (unsigned long long)a3);
+                    }
+                }
+                // LQ-IC: fp32 estimate against the slot's bound; the rare quartet that may beat it goes to the exact path
+                const float est = dev_log_score_f32(a1, c1[i], a3);
+                const float bound = slot[i] >= 0 ? ordered_to_float(*reinterpret_cast<volatile int*>(acc_b + slot[i])) : INFINITY;
+                if ((est == 1.f ? est : est - QS_EST_EPS) < bound) {
+                    unsigned long long q1, q2, q3;
+                    ordered_triple(rs[i], a.bifurcating, c0[i], c1[i], c2[i], q1, q2, q3);
+                    scan_candidate(q1, q2, q3, pair_key(ku[i], kv[i]), a.pair_best, a.pair_score, slot[i] >= 0 ? acc_b + slot[i] : nullptr, slot[i] >= 0 ? acc_t + slot[i] : nullptr);
+                }
+            }
+            if (RING) {
+                // hand the stage back: one arrival per warp; thread 0 refills it once every warp has arrived (the other warps run on
+                // into the stages that are already loaded — no CTA-wide barrier in the loop)
+                __syncwarp();
+                if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
+                if (tid == 0 && k + STAGES < n_chunks) {
+                    mbar_wait(&empty[stage], (empty_phase >> stage) & 1u);
+                    issue(k + STAGES);
+                }
+                if (tid == 0) empty_phase ^= 1u << stage;        // (phases of chunks that are not refilled complete too: every chunk gets WARPS arrivals)
             }
         }
         __syncthreads();
         // ---- flush the CTA's accumulators: one global atomic per touched key ----
         if (bif) {
+            auto flush = [&](int slot, long long key) {
+                unsigned long long* ps = a.pair_sums + (size_t)key * 3;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const unsigned long long v = (unsigned long long)acc_lo[k * n_acc + slot] | (CARRY ? (unsigned long long)acc_hi[k * n_acc + slot] << 32 : 0ull);
+                    if (v) atomicAdd(ps + k, v);
+                }
+            };
+            auto touched = [&](int y) -> bool {
+                uint32_t v = acc_lo[y] | acc_lo[n_acc + y] | acc_lo[2 * n_acc + y];
+                if (CARRY) v |= acc_hi[y] | acc_hi[n_acc + y] | acc_hi[2 * n_acc + y];
+                return v != 0;
+            };
             for (int x = tid; x < c; x += THREADS) {
-                const unsigned long long r1 = acc_s[x], r2 = acc_s[n_acc + x], r3 = acc_s[2 * (size_t)n_acc + x];
-                if (r1 | r2 | r3) {
-                    unsigned long long* ps = a.pair_sums + ((size_t)min(x, r) * a.I + max(x, r)) * 3;
-                    if (r1) atomicAdd(ps, r1);
-                    if (r2) atomicAdd(ps + 1, r2);
-                    if (r3) atomicAdd(ps + 2, r3);
-                }
-                const unsigned long long p1 = acc_s[n + x], p2 = acc_s[n_acc + n + x], p3 = acc_s[2 * (size_t)n_acc + n + x];
-                if (p1 | p2 | p3) {
-                    const int qq = acc_pq[x];
-                    unsigned long long* ps = a.pair_sums + ((size_t)min(x, qq) * a.I + max(x, qq)) * 3;
-                    if (p1) atomicAdd(ps, p1);
-                    if (p2) atomicAdd(ps + 1, p2);
-                    if (p3) atomicAdd(ps + 2, p3);
-                }
+                if (touched(x)) flush(x, pair_key(x, r));
+                if (touched(n + x)) flush(n + x, pair_key(x, (int)acc_pq[x]));
             }
             for (int x = tid; x < QS_Q4_SLOTS; x += THREADS) {
-                const unsigned long long t1 = acc_s[2 * n + x], t2 = acc_s[n_acc + 2 * n + x], t3 = acc_s[2 * (size_t)n_acc + 2 * n + x];
-                if (t1 | t2 | t3) {
+                if (touched(2 * n + x)) {
                     int i = (int)((1.f + sqrtf(1.f + 8.f * (float)x)) * 0.5f);
                     while (i * (i - 1) / 2 > x) --i;
                     while ((i + 1) * i / 2 <= x) ++i;
-                    const int jj = x - i * (i - 1) / 2;
-                    const int u = s_anc[i], v = s_anc[jj];
-                    unsigned long long* ps = a.pair_sums + ((size_t)min(u, v) * a.I + max(u, v)) * 3;
-                    if (t1) atomicAdd(ps, t1);
-                    if (t2) atomicAdd(ps + 1, t2);
-                    if (t3) atomicAdd(ps + 2, t3);
+                    flush(2 * n + x, pair_key(s_anc[i], s_anc[x - i * (i - 1) / 2]));
                 }
             }
         }

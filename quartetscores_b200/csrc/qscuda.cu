@@ -45,7 +45,7 @@ struct HostRef {
     std::vector<uint16_t> idepth;       // [I]
     // scan kernel (kernels/score.cuh): rows of lca[][] run-length encoded, parents in inner-index space
     std::vector<uint32_t> run_off, run_end, run_pd;
-    std::vector<int32_t> inner_parent, leaf_parent;
+    std::vector<int32_t> inner_parent, leaf_parent, inner_gap;
 };
 
 }  // namespace
@@ -53,6 +53,8 @@ struct HostRef {
 struct qs_ctx {
     int device = 0, n = 0, n_pad = 0, cint_bytes = 2, mode = 0, shard_index = 0, shard_count = 1;
     bool host_only = false;      // QS_DEVICE_NONE: reference bookkeeping + qs_score_finalize only
+    bool auto_mode = false;      // QS_MODE_AUTO: `mode` is re-decided by every qs_count (table if it fits this device, else table-free)
+    int* h_flags = nullptr;      // pinned: {max distance, tree error, |A|} read back asynchronously by qs_count
     int d_begin = 0, d_end = 0, num_sms = 148, smem_optin = 0;
     uint64_t rank_begin = 0, rank_end = 0;
     std::string err;
@@ -67,7 +69,7 @@ struct qs_ctx {
     uint16_t* d_lca = nullptr;
     uint16_t* d_idepth = nullptr;
     uint32_t *d_run_off = nullptr, *d_run_end = nullptr, *d_run_pd = nullptr;
-    int32_t *d_inner_parent = nullptr, *d_leaf_parent = nullptr;
+    int32_t *d_inner_parent = nullptr, *d_leaf_parent = nullptr, *d_inner_gap = nullptr;
     int32_t *d_inner_node = nullptr, *d_node_parent = nullptr, *d_node_depth = nullptr, *d_node_edge = nullptr, *d_node_inner = nullptr;
     long long* d_edge = nullptr;          // [4][E] edge minima / arg-minima of the per-edge reduction
     unsigned long long* d_edge_out = nullptr;   // [E][7]
@@ -146,23 +148,60 @@ int dev_alloc(qs_ctx* c, T** p, size_t count) {
     return QS_OK;
 }
 
-// balanced split of the rank space by the outer index d: boundary i = the d whose C(d,4) is closest to i/G of C(n,4)
-// (~ n * (i/G)^(1/4)); no alignment is required (the tiled kernel anchors its d-tiles at the shard's first d)
+// Split of the rank space by the outer index d into G contiguous ranges of (nearly) equal COUNTING COST — not equal
+// quartet counts: what a shard pays is the work items of the counting kernel (kernels/count_rows.cuh), i.e. 8 x 8 blocks
+// including their padding.  Per d: the role-X items of all c < d; per block of 8 consecutive d: the role-Y items of all
+// (b,c) below it, paid in full by every shard that touches the block (a shard boundary inside a d-block makes both
+// neighbours run it).  Measured item costs (round 1, class-B trees, profiles/r01_zj_*): 2.78e-5 ms per X item,
+// 2.12e-5 ms per Y item, hence the 0.76.  The boundaries minimise the largest shard cost (greedy fill under a
+// bisected threshold, exact for contiguous partitions of a monotone cost); pure function of (n, G): every rank computes
+// the same ranges.  (use_xo_diag is declared further down; its threshold is repeated here.)
 void shard_bounds(int n, int g, int G, int* d_begin, int* d_end) {
-    auto bound = [&](int i) -> int {
-        if (i <= 0) return 3;
-        if (i >= G) return n;
-        const long double target = (long double)binom4((uint64_t)n) * i / G;
-        int d = (int)((double)n * pow((double)i / G, 0.25));
-        d = std::min(n, std::max(3, d));
-        while (d < n && (long double)binom4((uint64_t)d) < target) ++d;
-        while (d > 3 && (long double)binom4((uint64_t)d - 1) >= target) --d;
-        // d is the smallest value with C(d,4) >= target; take d-1 if it is closer
-        if (d > 3 && target - (long double)binom4((uint64_t)d - 1) < (long double)binom4((uint64_t)d) - target) --d;
-        return std::min(n, std::max(3, d));
+    if (G <= 1) { *d_begin = 3; *d_end = n; return; }
+    const int xo_diag = n > 160 ? 1 : 0;
+    std::vector<double> PX(n + 1, 0.0), PYb((n >> 3) + 2, 0.0);
+    {
+        std::vector<double> A(n + 1, 0.0), B(n + 1, 0.0);       // prefix over c of the X items of one (c,d) / of the Y a-blocks of one (b,c)
+        for (int c = 2; c < n; ++c) {
+            const int nb = (c + 7) >> 3, nd = ((c - 2) >> 3) + 1;
+            const double items = nb * (nb - 1) / 2 + (xo_diag ? nd : 0.5 * nd);      // XO blocks (+ diagonal blocks: XO items or half-cost XD items)
+            A[c + 1] = A[c] + items;
+            double bc = 0;
+            for (int bb = 1; bb < c; ++bb) bc += (bb + 7) >> 3;
+            B[c + 1] = B[c] + bc;
+        }
+        for (int d = 3; d < n; ++d) PX[d + 1] = PX[d] + A[d];                          // X items with this d: all c < d
+        for (int k = 0; k <= (n - 1) >> 3; ++k) {                                       // Y items of d-block k: all (b,c) with c + 1 <= 8k + 7
+            const int cmax = std::min(8 * k + 6, n - 2);
+            PYb[k + 1] = PYb[k] + (cmax >= 2 ? 0.76 * B[cmax + 1] : 0.0);
+        }
+    }
+    auto cost = [&](int b, int e) -> double {                                           // shard [b, e), b < e
+        return PX[e] - PX[b] + (PYb[((e - 1) >> 3) + 1] - PYb[b >> 3]);
     };
-    *d_begin = bound(g);
-    *d_end = bound(g + 1);
+    // smallest threshold T for which greedy filling needs <= G shards
+    auto fill = [&](double T, std::vector<int>* out) -> int {
+        int cnt = 0, b = 3;
+        while (b < n) {
+            int e = b + 1;
+            while (e < n && cost(b, e + 1) <= T) ++e;
+            ++cnt; b = e;
+            if (out) out->push_back(e);
+            if (cnt > G) return cnt;
+        }
+        return cnt;
+    };
+    double lo = 0, hi = cost(3, n);
+    for (int it = 0; it < 60; ++it) {
+        const double mid = 0.5 * (lo + hi);
+        if (fill(mid, nullptr) <= G) hi = mid; else lo = mid;
+    }
+    std::vector<int> ends;
+    fill(hi, &ends);
+    while ((int)ends.size() < G) ends.push_back(n);                                     // fewer d values than shards: the last shards are empty
+    ends[G - 1] = n;
+    *d_begin = g == 0 ? 3 : ends[g - 1];
+    *d_end = ends[g];
     if (*d_end < *d_begin) *d_end = *d_begin;
 }
 
@@ -184,7 +223,7 @@ uint64_t cint_mask(int bytes) { return bytes >= 8 ? ~0ull : ((1ull << (8 * bytes
 
 void free_all(qs_ctx* c) {
     cudaFree(c->d_lca); cudaFree(c->d_idepth);
-    cudaFree(c->d_run_off); cudaFree(c->d_run_end); cudaFree(c->d_run_pd); cudaFree(c->d_inner_parent); cudaFree(c->d_leaf_parent);
+    cudaFree(c->d_run_off); cudaFree(c->d_run_end); cudaFree(c->d_run_pd); cudaFree(c->d_inner_parent); cudaFree(c->d_leaf_parent); cudaFree(c->d_inner_gap);
     cudaFree(c->d_inner_node); cudaFree(c->d_node_parent); cudaFree(c->d_node_depth); cudaFree(c->d_node_edge); cudaFree(c->d_node_inner);
     cudaFree(c->d_edge); cudaFree(c->d_edge_out); cudaFree(c->d_scan_scratch); cudaFree(c->d_scan_counter);
     cudaFree(c->d_off); cudaFree(c->d_parent); cudaFree(c->d_leaf);
@@ -192,6 +231,7 @@ void free_all(qs_ctx* c) {
     cudaFree(c->d_class); cudaFree(c->d_order); cudaFree(c->d_nA); cudaFree(c->d_counter);
     cudaFree(c->d_tasks); cudaFree(c->d_enum);
     cudaFree(c->d_pair_sums); cudaFree(c->d_pair_best); cudaFree(c->d_pair_score); cudaFree(c->d_pair_score_local);
+    if (c->h_flags) cudaFreeHost(c->h_flags);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
 }
@@ -379,8 +419,11 @@ int upload_plan(qs_ctx* c, const HostPlan& P) {
     return QS_OK;
 }
 
-// role-Y tasks are only needed (and only planned) when some gene tree is class B
-bool plan_needs_y(const qs_ctx* c) { return c->n_class_a < c->m; }
+// Role-Y tasks are only needed when some gene tree is class B.  A table-free run plans a task table per slab and per step
+// (up to ~1e6 tasks at n = 2000), so it reads the class split back first and leaves role Y out when every tree is class A;
+// a table context plans once, always with role Y (the kernel skips the class-B task space when |B| = 0), and never waits
+// for the class split.
+bool plan_needs_y(const qs_ctx* c) { return c->mode != QS_MODE_TABLE_FREE || c->n_class_a < c->m; }
 
 int ensure_plan(qs_ctx* c, int dB, int dE, const HostPlan* ready = nullptr) {
     const int with_y = plan_needs_y(c) ? 1 : 0, threads = cr_threads_for(c->n);
@@ -545,7 +588,7 @@ int build_reference(qs_ctx* c, int n_nodes, const int32_t* parent, const int32_t
             else order.emplace_back(n + (unary++), v);
         }
         std::sort(order.begin(), order.end());
-        for (auto& o : order) { R.inner_index[o.second] = (int)R.inner_node.size(); R.inner_node.push_back(o.second); }
+        for (auto& o : order) { R.inner_index[o.second] = (int)R.inner_node.size(); R.inner_node.push_back(o.second); R.inner_gap.push_back(o.first); }
     }
     R.n_inner = (int)R.inner_node.size();
     R.bifurcating = (max_rank == 2);
@@ -612,15 +655,14 @@ int clear_pair_arrays(qs_ctx* c) {
     return fill_i64(c, c->d_pair_score, I * I, QS_I64_NONE);
 }
 
-// CTA shape of the scan: a CTA owns one (c,d) and its threads the row pairs (b, c-1-b), so 256 threads cover c <= 512 in one
-// pass; 512 threads for wider references.  The per-CTA accumulators live in shared memory while they fit beside the rings.
+// CTA shape of the scan: a CTA owns one (c,d), lanes take consecutive table entries.  512 threads (two CTAs per SM) while the
+// per-CTA accumulators (36 bytes per slot, 2n + 496 slots) fit twice beside the staging rings, 1024 threads above that; for
+// very wide references (n > ~2,300) the accumulators move to global memory.
 template <typename CINT, int THREADS>
-int launch_scan_t(qs_ctx* c, ScoreArgs& a) {
-    const size_t ring = scan_ring_bytes(THREADS), acc = scan_acc_bytes(c->n);
-    bool smem_acc = ring + acc + 1024 <= (size_t)c->smem_optin;
-    if (getenv("QS_SCAN_GLOBAL_ACC")) smem_acc = false;                                   // test hook: the large-n path on a small input
+int launch_scan_t(qs_ctx* c, ScoreArgs& a, bool smem_acc) {
+    const size_t ring = scan_ring_bytes(THREADS, (int)sizeof(CINT)), acc = scan_acc_bytes(c->n);
     const size_t smem = ring + (smem_acc ? acc : 0);
-    int per_sm = std::max(1, std::min(2048 / THREADS, (int)((size_t)c->smem_optin / (smem + 1024))));
+    int per_sm = std::max(1, std::min(THREADS <= 512 ? 2 : 1, (int)((size_t)c->smem_optin / (smem + 1024))));
     const int grid = (int)std::max<long long>(1, std::min<long long>(a.n_items, (long long)c->num_sms * per_sm));
     if (!smem_acc) {
         const size_t need = (size_t)grid * acc;
@@ -632,13 +674,18 @@ int launch_scan_t(qs_ctx* c, ScoreArgs& a) {
         a.scratch = c->d_scan_scratch;
     }
     QS_CUDA(c, cudaMemsetAsync(c->d_scan_counter, 0, sizeof(int), c->stream));
-    if (smem_acc) {
-        QS_CUDA(c, cudaFuncSetAttribute(qs_scan_rows_kernel<CINT, THREADS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        qs_scan_rows_kernel<CINT, THREADS, true><<<grid, THREADS, smem, c->stream>>>(a);
-    } else {
-        QS_CUDA(c, cudaFuncSetAttribute(qs_scan_rows_kernel<CINT, THREADS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        qs_scan_rows_kernel<CINT, THREADS, false><<<grid, THREADS, smem, c->stream>>>(a);
-    }
+    // can a 32-bit sum overflow inside one (c,d)?  largest stored count x the C(c,2) quartets of the widest pair
+    const uint64_t max_count = std::min<uint64_t>((uint64_t)c->m * (uint64_t)a.count_scale, a.cint_mask);
+    const bool carry = max_count * binom2((uint64_t)std::max(2, a.d_end - 1)) >= (1ull << 32) || getenv("QS_SCAN_CARRY") != nullptr;      // (env: test hook)
+    auto go = [&](auto kernel) -> int {
+        QS_CUDA(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kernel<<<grid, THREADS, smem, c->stream>>>(a);
+        return QS_OK;
+    };
+    int rr;
+    if (smem_acc) rr = carry ? go(qs_scan_kernel<CINT, THREADS, true, true>) : go(qs_scan_kernel<CINT, THREADS, true, false>);
+    else rr = carry ? go(qs_scan_kernel<CINT, THREADS, false, true>) : go(qs_scan_kernel<CINT, THREADS, false, false>);
+    if (rr) return rr;
     c->launches++;
     QS_CUDA(c, cudaGetLastError());
     return QS_OK;
@@ -646,7 +693,12 @@ int launch_scan_t(qs_ctx* c, ScoreArgs& a) {
 
 template <typename CINT>
 int launch_scan(qs_ctx* c, ScoreArgs& a) {
-    return c->n <= 1024 ? launch_scan_t<CINT, 256>(c, a) : launch_scan_t<CINT, 512>(c, a);
+    const size_t acc = scan_acc_bytes(c->n), optin = (size_t)c->smem_optin;
+    const bool force_global = getenv("QS_SCAN_GLOBAL_ACC") != nullptr;                    // test hook: the large-n path on a small input
+    int threads = (2 * (scan_ring_bytes(512, (int)sizeof(CINT)) + acc + 1024) <= optin) ? 512 : 1024;
+    if (const char* env = getenv("QS_SCAN_THREADS")) { const int t = atoi(env); if (t == 512 || t == 1024) threads = t; }    // tuning / test hook
+    if (threads == 512) return launch_scan_t<CINT, 512>(c, a, !force_global && scan_ring_bytes(512, (int)sizeof(CINT)) + acc + 1024 <= optin);
+    return launch_scan_t<CINT, 1024>(c, a, !force_global && scan_ring_bytes(1024, (int)sizeof(CINT)) + acc + 1024 <= optin);
 }
 
 // scan a table holding the quartets with d in [dB, dE) and accumulate into the per-pair partials on the device
@@ -656,7 +708,7 @@ int scan_table(qs_ctx* c, const void* table, int dB, int dE, int count_scale) {
     if (a.n_items == 0) return QS_OK;
     if (a.n_items > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "scan work-item count overflow");
     a.table = table; a.rank_base = binom4((uint64_t)dB); a.lca = c->d_lca; a.idepth = c->d_idepth;
-    a.run_off = c->d_run_off; a.run_end = c->d_run_end; a.run_pd = c->d_run_pd; a.inner_parent = c->d_inner_parent; a.leaf_parent = c->d_leaf_parent;
+    a.run_off = c->d_run_off; a.run_end = c->d_run_end; a.run_pd = c->d_run_pd; a.inner_parent = c->d_inner_parent; a.leaf_parent = c->d_leaf_parent; a.inner_gap = c->d_inner_gap;
     a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.pair_score = c->d_pair_score; a.scratch = nullptr; a.work_counter = c->d_scan_counter;
     a.n = c->n; a.I = c->ref.n_inner;
     a.d_begin = dB; a.d_end = dE; a.count_scale = count_scale; a.cint_mask = cint_mask(c->cint_bytes);
@@ -669,19 +721,9 @@ int scan_table(qs_ctx* c, const void* table, int dB, int dE, int count_scale) {
     }
 }
 
-// QS_MODE_TABLE_FREE (the -s analogue): the shard's d-range is processed in slabs that fit the device; each slab is
-// counted into a temporary table, scanned into the per-pair partials and discarded
-int run_table_free(qs_ctx* c) {
-    if (!c->has_ref) QS_FAIL(c, QS_E_STATE, "a table-free context scores while it counts: call qs_set_reference before qs_count");
-    int r;
-    if ((r = ensure_pair_arrays(c))) return r;
-    if ((r = clear_pair_arrays(c))) return r;
-    size_t free_b = 0, total_b = 0;
-    QS_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-    size_t budget = (free_b + c->table_bytes) / 10 * 6;                 // leave room for the distance matrices of a later, larger run
-    if (const char* env = getenv("QS_SLAB_BYTES")) budget = (size_t)strtoull(env, nullptr, 10);   // test hook: force several slabs
+// slabs of a table-free run: largest dE (8-aligned when possible, so that role Y's d-blocks are full) whose table fits the budget
+std::vector<std::pair<int, int>> plan_slabs(const qs_ctx* c, size_t budget) {
     const size_t eb = 3 * (size_t)c->cint_bytes;
-    // slabs: largest dE (8-aligned when possible, so that role Y's d-blocks are full) whose table fits the budget
     std::vector<std::pair<int, int>> slabs;
     for (int dB = std::max(3, c->d_begin); dB < c->d_end;) {
         int dE = dB + 1;
@@ -690,6 +732,38 @@ int run_table_free(qs_ctx* c) {
         slabs.emplace_back(dB, dE);
         dB = dE;
     }
+    return slabs;
+}
+
+size_t slab_budget(const qs_ctx* c) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); free_b = (size_t)8 << 30; }
+    size_t budget = (free_b + c->table_bytes) / 10 * 6;                 // leave room for the distance matrices of a later, larger run
+    if (const char* env = getenv("QS_SLAB_BYTES")) budget = (size_t)strtoull(env, nullptr, 10);   // test hook: force several slabs
+    return budget;
+}
+
+int ensure_slab_table(qs_ctx* c, size_t need, int dB, int dE) {
+    if (need <= c->table_bytes) return QS_OK;
+    if (c->d_table) { cudaFree(c->d_table); c->d_table = nullptr; c->table_bytes = 0; }
+    cudaError_t e = cudaMalloc(&c->d_table, need + kTableSlack);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        QS_FAIL(c, QS_E_MEMORY, "Insufficient memory! a slab of %zu bytes (d in [%d,%d)) does not fit this device", need, dB, dE);
+    }
+    c->table_bytes = need;
+    return QS_OK;
+}
+
+// QS_MODE_TABLE_FREE (the -s analogue): the shard's d-range is processed in slabs that fit the device; each slab is
+// counted into a temporary table, scanned into the per-pair partials and discarded
+int run_table_free(qs_ctx* c) {
+    if (!c->has_ref) QS_FAIL(c, QS_E_STATE, "a table-free context scores while it counts: call qs_set_reference before qs_count");
+    int r;
+    if ((r = ensure_pair_arrays(c))) return r;
+    if ((r = clear_pair_arrays(c))) return r;
+    const size_t eb = 3 * (size_t)c->cint_bytes;
+    const std::vector<std::pair<int, int>> slabs = plan_slabs(c, slab_budget(c));
     // the host plan of slab k+1 (task table: up to ~1e6 tasks at n = 2000) is built by a helper thread while the GPU counts slab k
     const bool with_y = plan_needs_y(c);
     HostPlan plans[2];
@@ -708,23 +782,37 @@ int run_table_free(qs_ctx* c) {
         planner.join();
         start_plan(k + 1);
         const size_t need = (size_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB)) * eb;
-        if (need > c->table_bytes) {
-            if (c->d_table) { cudaFree(c->d_table); c->d_table = nullptr; c->table_bytes = 0; }
-            cudaError_t e = cudaMalloc(&c->d_table, need + kTableSlack);
-            if (e != cudaSuccess) {
-                cudaGetLastError();
-                char b_[256];
-                snprintf(b_, sizeof b_, "Insufficient memory! a slab of %zu bytes (d in [%d,%d)) does not fit this device", need, dB, dE);
-                c->err = b_; rc = QS_E_MEMORY; break;
-            }
-            c->table_bytes = need;
-        }
+        if ((rc = ensure_slab_table(c, need, dB, dE))) break;
         if ((rc = run_count_rows(c, dB, dE, c->d_table, &plans[k & 1]))) break;
         rc = scan_table(c, c->d_table, dB, dE, c->fused_scale);
     }
     if (planner.joinable()) planner.join();
     if (rc) return rc;
     c->fused_partials_valid = true;
+    return QS_OK;
+}
+
+// canonical counts of the ranks [lo, hi) of this shard into host memory.  Table contexts copy them; a table-free context
+// keeps no table, so the slabs that cover the range are counted again (the distance matrices are still on the device).
+int counts_to_host(qs_ctx* c, uint64_t lo, uint64_t hi, void* out) {
+    const size_t eb = 3 * (size_t)c->cint_bytes;
+    if (lo >= hi) return QS_OK;
+    if (c->mode == QS_MODE_TABLE) {
+        QS_CUDA(c, cudaMemcpyAsync(out, (const char*)c->d_table + (lo - c->rank_begin) * eb, (hi - lo) * eb, cudaMemcpyDeviceToHost, c->stream));
+        QS_CUDA(c, cudaStreamSynchronize(c->stream));
+        return QS_OK;
+    }
+    if (!c->dist_valid) QS_FAIL(c, QS_E_STATE, "table-free context: the distance matrices are gone, call qs_count again");
+    int r;
+    for (auto& sl : plan_slabs(c, slab_budget(c))) {
+        const uint64_t rb = binom4((uint64_t)sl.first), re = binom4((uint64_t)sl.second);
+        const uint64_t a = std::max(lo, rb), b = std::min(hi, re);
+        if (a >= b) continue;
+        if ((r = ensure_slab_table(c, (size_t)(re - rb) * eb, sl.first, sl.second))) return r;
+        if ((r = run_count_rows(c, sl.first, sl.second, c->d_table))) return r;
+        QS_CUDA(c, cudaMemcpyAsync((char*)out + (a - lo) * eb, (const char*)c->d_table + (a - rb) * eb, (b - a) * eb, cudaMemcpyDeviceToHost, c->stream));
+        QS_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
     return QS_OK;
 }
 
@@ -948,12 +1036,13 @@ int qs_create(qs_ctx** out, int n_taxa, int cint_bytes, int mode, int device, in
     *out = nullptr;
     if (n_taxa < 4 || n_taxa > 32768) return QS_E_ARG;
     if (cint_bytes != 1 && cint_bytes != 2 && cint_bytes != 4 && cint_bytes != 8) return QS_E_ARG;
-    if (mode != QS_MODE_TABLE && mode != QS_MODE_TABLE_FREE) return QS_E_ARG;
+    if (mode != QS_MODE_TABLE && mode != QS_MODE_TABLE_FREE && mode != QS_MODE_AUTO) return QS_E_ARG;
     if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return QS_E_ARG;
     if (device == QS_DEVICE_NONE) {
         // host-only context: no CUDA call at all; only qs_set_reference / qs_score_finalize / qs_shard_range work on it
         qs_ctx* c = new qs_ctx();
-        c->host_only = true; c->device = device; c->n = n_taxa; c->n_pad = (n_taxa + 7) / 8 * 8; c->cint_bytes = cint_bytes; c->mode = mode;
+        c->host_only = true; c->device = device; c->n = n_taxa; c->n_pad = (n_taxa + 7) / 8 * 8; c->cint_bytes = cint_bytes;
+        c->auto_mode = mode == QS_MODE_AUTO; c->mode = c->auto_mode ? QS_MODE_TABLE : mode;
         c->shard_index = shard_index; c->shard_count = shard_count;
         shard_bounds(n_taxa, shard_index, shard_count, &c->d_begin, &c->d_end);
         c->rank_begin = binom4((uint64_t)c->d_begin); c->rank_end = binom4((uint64_t)c->d_end);
@@ -967,7 +1056,8 @@ int qs_create(qs_ctx** out, int n_taxa, int cint_bytes, int mode, int device, in
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return QS_E_CUDA;
     if (prop.major < 10) return QS_E_CUDA;   // sm_100a code only
     qs_ctx* c = new qs_ctx();
-    c->device = device; c->n = n_taxa; c->n_pad = (n_taxa + 7) / 8 * 8; c->cint_bytes = cint_bytes; c->mode = mode;
+    c->device = device; c->n = n_taxa; c->n_pad = (n_taxa + 7) / 8 * 8; c->cint_bytes = cint_bytes;
+    c->auto_mode = mode == QS_MODE_AUTO; c->mode = c->auto_mode ? QS_MODE_TABLE : mode;
     c->shard_index = shard_index; c->shard_count = shard_count;
     c->num_sms = prop.multiProcessorCount; c->smem_optin = (int)prop.sharedMemPerBlockOptin;
     shard_bounds(n_taxa, shard_index, shard_count, &c->d_begin, &c->d_end);
@@ -976,7 +1066,7 @@ int qs_create(qs_ctx** out, int n_taxa, int cint_bytes, int mode, int device, in
     c->stream = c->own_stream;
     for (auto& e : c->ev) if (cudaEventCreate(&e) != cudaSuccess) { free_all(c); delete c; return QS_E_CUDA; }
     if (cudaMalloc((void**)&c->d_flags, 2 * sizeof(int)) != cudaSuccess || cudaMalloc((void**)&c->d_nA, sizeof(int32_t)) != cudaSuccess ||
-        cudaMalloc((void**)&c->d_counter, sizeof(int)) != cudaSuccess) { free_all(c); delete c; return QS_E_CUDA; }
+        cudaMalloc((void**)&c->d_counter, sizeof(int)) != cudaSuccess || cudaMallocHost((void**)&c->h_flags, 4 * sizeof(int)) != cudaSuccess) { free_all(c); delete c; return QS_E_CUDA; }
     *out = c;
     return QS_OK;
 }
@@ -1026,7 +1116,7 @@ int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int3
             return QS_OK;
         };
         if ((r = up(&ctx->d_run_off, R.run_off)) || (r = up(&ctx->d_run_end, R.run_end)) || (r = up(&ctx->d_run_pd, R.run_pd)) ||
-            (r = up(&ctx->d_inner_parent, R.inner_parent)) || (r = up(&ctx->d_leaf_parent, R.leaf_parent)) || (r = up(&ctx->d_inner_node, R.inner_node)) ||
+            (r = up(&ctx->d_inner_parent, R.inner_parent)) || (r = up(&ctx->d_leaf_parent, R.leaf_parent)) || (r = up(&ctx->d_inner_gap, R.inner_gap)) || (r = up(&ctx->d_inner_node, R.inner_node)) ||
             (r = up(&ctx->d_node_parent, R.parent)) || (r = up(&ctx->d_node_depth, R.depth)) || (r = up(&ctx->d_node_edge, R.parent_edge)) ||
             (r = up(&ctx->d_node_inner, R.inner_index)))
             return r;
@@ -1115,24 +1205,38 @@ int qs_count(qs_ctx* ctx) {
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
     if ((r = run_distances(ctx))) return r;
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    // the class split decides the task table (no role-Y tasks are planned when every tree is class A) and a malformed
-    // tree should fail before the long kernel, so the host waits for the distance kernels here (they are < 1 % of a step)
-    int flags[2] = {0, 0};
-    int32_t nA = 0;
-    QS_CUDA(ctx, cudaMemcpyAsync(flags, ctx->d_flags, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
-    QS_CUDA(ctx, cudaMemcpyAsync(&nA, ctx->d_nA, sizeof(nA), cudaMemcpyDeviceToHost, ctx->stream));
-    QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->n_class_a = nA; ctx->counted_once = true;
-    if (flags[1] != 0) QS_FAIL(ctx, QS_E_TREE, "malformed evaluation tree (code %d): need parent[i] < i, leaf ids in [0,n) exactly on leaves, each taxon at most once per tree", flags[1]);
-    if (flags[0] > kMaxHalfExact) QS_FAIL(ctx, QS_E_UNSUPPORTED, "an evaluation tree has a leaf-to-leaf path of %d edges; this build packs distances in fp16 (exact up to %d)", flags[0], kMaxHalfExact);
+    // error flags and the class split come back asynchronously (pinned buffer); they are looked at when the stream is drained
+    QS_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags, ctx->d_flags, 2 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    QS_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 2, ctx->d_nA, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    auto check_flags = [&]() -> int {
+        ctx->n_class_a = ctx->h_flags[2]; ctx->counted_once = true;
+        if (ctx->h_flags[1] != 0) QS_FAIL(ctx, QS_E_TREE, "malformed evaluation tree (code %d): need parent[i] < i, leaf ids in [0,n) exactly on leaves, each taxon at most once per tree", ctx->h_flags[1]);
+        if (ctx->h_flags[0] > kMaxHalfExact) QS_FAIL(ctx, QS_E_UNSUPPORTED, "an evaluation tree has a leaf-to-leaf path of %d edges; this build packs distances in fp16 (exact up to %d)", ctx->h_flags[0], kMaxHalfExact);
+        return QS_OK;
+    };
     const uint64_t nq = ctx->rank_end - ctx->rank_begin;
+    const size_t need = (size_t)nq * 3 * ctx->cint_bytes;
+    if (ctx->auto_mode) {                                     // QS_MODE_AUTO: keep the shard's table resident if it fits beside the matrices
+        size_t free_b = 0, total_b = 0;
+        QS_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
+        size_t limit = free_b + ctx->table_bytes > ((size_t)1 << 30) ? free_b + ctx->table_bytes - ((size_t)1 << 30) : 0;
+        if (const char* env = getenv("QS_TABLE_BYTES_LIMIT")) limit = (size_t)strtoull(env, nullptr, 10);      // test hook
+        const int want = need + kTableSlack <= limit ? QS_MODE_TABLE : QS_MODE_TABLE_FREE;
+        if (want != ctx->mode && ctx->d_table) { cudaFree(ctx->d_table); ctx->d_table = nullptr; ctx->table_bytes = 0; }
+        ctx->mode = want;
+    }
+    if (ctx->mode == QS_MODE_TABLE_FREE) {
+        // (the class split decides whether the slabs' task tables carry role Y, and a malformed tree should fail before minutes of
+        // counting: one wait for the distance kernels, < 1 % of such a step)
+        QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if ((r = check_flags())) return r;
+    }
     QS_CUDA(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     if (ctx->mode == QS_MODE_TABLE) {
-        const size_t need = (size_t)nq * 3 * ctx->cint_bytes;
         if (need > ctx->table_bytes) {
             if (ctx->d_table) { cudaFree(ctx->d_table); ctx->d_table = nullptr; ctx->table_bytes = 0; }
             cudaError_t e = cudaMalloc(&ctx->d_table, need + kTableSlack);
-            if (e != cudaSuccess) { cudaGetLastError(); QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! count table of %zu bytes does not fit this device (use QS_MODE_TABLE_FREE or more shards)", need); }
+            if (e != cudaSuccess) { cudaGetLastError(); QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! count table of %zu bytes does not fit this device (use QS_MODE_AUTO / QS_MODE_TABLE_FREE or more shards)", need); }
             ctx->table_bytes = need;
         }
         if ((r = run_count_rows(ctx, ctx->d_begin, ctx->d_end, ctx->d_table))) return r;
@@ -1144,6 +1248,7 @@ int qs_count(qs_ctx* ctx) {
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]); ctx->dist_ms = ms;
     cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->count_ms = ms;
+    if ((r = check_flags())) return r;
     ctx->counted = true;
     return QS_OK;
 }
@@ -1151,6 +1256,17 @@ int qs_count(qs_ctx* ctx) {
 int qs_score_num_pairs(const qs_ctx* ctx, int64_t* n_pairs) {
     if (!ctx || !n_pairs) return QS_E_ARG;
     *n_pairs = (int64_t)ctx->ref.n_inner * ctx->ref.n_inner;
+    return QS_OK;
+}
+
+int qs_score_inner_nodes(const qs_ctx* ctx, int32_t* node_of_inner, int64_t capacity, int64_t* n_inner) {
+    if (!ctx || !n_inner) return QS_E_ARG;
+    if (!ctx->has_ref) return QS_E_STATE;
+    *n_inner = ctx->ref.n_inner;
+    if (node_of_inner) {
+        if (capacity < ctx->ref.n_inner) return QS_E_ARG;
+        memcpy(node_of_inner, ctx->ref.inner_node.data(), (size_t)ctx->ref.n_inner * sizeof(int32_t));
+    }
     return QS_OK;
 }
 
@@ -1292,17 +1408,12 @@ int qs_shard_range(const qs_ctx* ctx, uint64_t* rank_begin, uint64_t* rank_end) 
 int qs_get_counts(qs_ctx* ctx, uint64_t rank_begin, uint64_t rank_end, void* out) {
     if (!ctx || !out || rank_end < rank_begin) return QS_E_ARG;
     if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
-    if (ctx->mode != QS_MODE_TABLE) QS_FAIL(ctx, QS_E_STATE, "table-free context keeps no table");
     if (!ctx->counted) QS_FAIL(ctx, QS_E_STATE, "qs_count has not been called");
     QS_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t eb = 3 * (size_t)ctx->cint_bytes;
     memset(out, 0, (rank_end - rank_begin) * eb);
     const uint64_t lo = std::max(rank_begin, ctx->rank_begin), hi = std::min(rank_end, ctx->rank_end);
-    if (lo < hi) {
-        QS_CUDA(ctx, cudaMemcpyAsync((char*)out + (lo - rank_begin) * eb, (const char*)ctx->d_table + (lo - ctx->rank_begin) * eb, (hi - lo) * eb,
-                                     cudaMemcpyDeviceToHost, ctx->stream));
-        QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+    if (lo < hi) return counts_to_host(ctx, lo, hi, (char*)out + (lo - rank_begin) * eb);
     return QS_OK;
 }
 
@@ -1432,17 +1543,42 @@ int qs_get_distances(qs_ctx* ctx, int64_t tree, uint16_t* out) {
 }
 
 int qs_write_raw_qic(qs_ctx* ctx, int count_scale, const char* const* taxon_names, const char* path) {
-    if (!ctx || !taxon_names || !path) return QS_E_ARG;
-    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
-    if (ctx->mode != QS_MODE_TABLE || ctx->shard_count != 1) QS_FAIL(ctx, QS_E_STATE, "raw QIC needs a single-shard table context");
-    if (!ctx->counted || !ctx->has_ref) QS_FAIL(ctx, QS_E_STATE, "needs qs_set_reference and qs_count");
+    if (!ctx) return QS_E_ARG;
+    if (ctx->shard_count != 1) QS_FAIL(ctx, QS_E_STATE, "this context holds shard %d of %d: pass all shards to qs_write_raw_qic_shards", ctx->shard_index, ctx->shard_count);
+    qs_ctx* one[1] = {ctx};
+    return qs_write_raw_qic_shards(one, 1, count_scale, taxon_names, path);
+}
+
+int qs_write_raw_qic_shards(qs_ctx* const* ctxs, int n_ctxs, int count_scale, const char* const* taxon_names, const char* path) {
+    if (!ctxs || n_ctxs < 1 || !ctxs[0] || !taxon_names || !path) return QS_E_ARG;
+    qs_ctx* ctx = ctxs[0];
     if (count_scale != 1 && count_scale != 2) return QS_E_ARG;
-    QS_CUDA(ctx, cudaSetDevice(ctx->device));
-    const uint64_t nq = ctx->rank_end - ctx->rank_begin;
+    // the shards must tile the whole rank space in order
+    uint64_t next = 0;
+    for (int g = 0; g < n_ctxs; ++g) {
+        qs_ctx* c = ctxs[g];
+        if (!c) return QS_E_ARG;
+        if (c->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
+        if (c->n != ctx->n || c->cint_bytes != ctx->cint_bytes || c->rank_begin != next) QS_FAIL(ctx, QS_E_ARG, "context %d does not continue the rank space at %llu", g, (unsigned long long)next);
+        if (!c->counted) QS_FAIL(ctx, QS_E_STATE, "needs qs_count on every shard");
+        next = c->rank_end;
+    }
+    if (next != binom4((uint64_t)ctx->n)) QS_FAIL(ctx, QS_E_ARG, "the contexts do not cover all C(n,4) quartets");
+    if (!ctx->has_ref) QS_FAIL(ctx, QS_E_STATE, "needs qs_set_reference");
+    // the file is ordered by (a,b,c,d) with a outermost, the table by rank with d outermost: the whole table is gathered on
+    // the host first (a table-free shard counts its slabs again for this, see counts_to_host)
+    const uint64_t nq = next;
     const size_t eb = (size_t)ctx->cint_bytes;
-    std::vector<unsigned char> tab((size_t)nq * 3 * eb);
-    QS_CUDA(ctx, cudaMemcpyAsync(tab.data(), ctx->d_table, tab.size(), cudaMemcpyDeviceToHost, ctx->stream));
-    QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    std::vector<unsigned char> tab;
+    try { tab.resize((size_t)nq * 3 * eb); } catch (const std::exception&) {
+        QS_FAIL(ctx, QS_E_MEMORY, "Insufficient memory! the raw QIC dump gathers the whole table (%llu bytes) in host memory", (unsigned long long)(nq * 3 * eb));
+    }
+    for (int g = 0; g < n_ctxs; ++g) {
+        qs_ctx* c = ctxs[g];
+        QS_CUDA(ctx, cudaSetDevice(c->device));
+        int r = counts_to_host(c, c->rank_begin, c->rank_end, tab.data() + (size_t)c->rank_begin * 3 * eb);
+        if (r) { if (c != ctx) ctx->err = c->err; return r; }
+    }
     FILE* f = fopen(path, "w");
     if (!f) QS_FAIL(ctx, QS_E_ARG, "cannot open %s for writing", path);
     const HostRef& R = ctx->ref;
@@ -1465,7 +1601,7 @@ int qs_write_raw_qic(qs_ctx* ctx, int count_scale, const char* const* taxon_name
                 const int dr = R.idepth[R.lca[(size_t)cc * n + d]];
                 const int S0 = dp + dr, S2 = std::min(dp, std::min(dq, dr)) + dq;
                 if (S0 == S2) continue;                                   // unresolved in the reference tree (:559-562)
-                const uint64_t rk = (quartet_rank(a, b, cc, d) - ctx->rank_begin) * 3;
+                const uint64_t rk = quartet_rank(a, b, cc, d) * 3;
                 const uint64_t c0 = get(rk), c1 = get(rk + 1), c2 = get(rk + 2);
                 int len;
                 if (S0 > S2) len = snprintf(line, sizeof line, "(%s,%s|%s,%s): %g\n", taxon_names[a], taxon_names[b], taxon_names[cc], taxon_names[d], host_log_score(c0, c1, c2));

@@ -6,7 +6,8 @@ import _oracle as O
 
 
 class RefPairs:
-    def __init__(self, ref):
+    def __init__(self, ref, inner_nodes=None):
+        """inner_nodes: Context.inner_nodes() (the library's own order); default: the documented rule restated here"""
         self.ref = ref
         N, n = ref.n_nodes, ref.n_taxa
         lo, hi = np.full(N, 1 << 30), np.full(N, -1)
@@ -27,6 +28,8 @@ class RefPairs:
         # inner index = rank of the node's first gap in the planar leaf order (qscuda.cu build_reference); single-child nodes last
         key = {v: (hi[self.kids[v][0]] - 1 if len(self.kids[v]) >= 2 else n + v) for v in self.inner}
         self.iidx = {v: i for i, v in enumerate(sorted(self.inner, key=lambda v: key[v]))}
+        if inner_nodes is not None:
+            assert [int(v) for v in inner_nodes] == sorted(self.inner, key=lambda v: key[v]), "inner-node order differs from the documented rule"
         self.full = frozenset(range(n))
 
     def link_sets(self, x):

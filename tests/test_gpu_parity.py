@@ -449,3 +449,47 @@ def test_lq_selection_count_limit_is_refused_not_wrapped():
         with pytest.raises(QSError) as e:
             ctx.score(2)                                               # m * 2 = 2^21
         assert e.value.code == -6
+
+
+def test_auto_mode_and_table_free_counts_export(golden, monkeypatch, tmp_path):
+    """QS_MODE_AUTO picks the resident table when it fits and table-free slabs when it does not (forced); a table-free context
+    still answers qs_get_counts / writes the -q file by counting the covering slabs again."""
+    from quartetscores_b200 import QS_MODE_AUTO, QS_MODE_TABLE_FREE
+    g = golden("s32x270_spr")
+    _, ref, flat = load_input(g)
+    want = g["counts"].astype(np.uint32)
+    monkeypatch.setenv("QS_SLAB_BYTES", "30000")
+    for mode, limit in ((QS_MODE_AUTO, None), (QS_MODE_AUTO, "1000"), (QS_MODE_TABLE_FREE, None)):
+        if limit:
+            monkeypatch.setenv("QS_TABLE_BYTES_LIMIT", limit)
+        with Context(ref.n_taxa, 2, mode=mode) as ctx:
+            ctx.set_reference(ref)
+            ctx.add_trees(flat)
+            ctx.count()
+            assert np.array_equal(ctx.get_counts().astype(np.uint32), want)
+            assert np.array_equal(ctx.get_counts(1000, 1700).astype(np.uint32), want[1000:1700])
+            lq, qp, eqp = ctx.score(1)
+            assert np.allclose(lq[np.isfinite(lq)], g["lqic"][np.isfinite(g["lqic"])], rtol=0, atol=1e-9)
+            p = str(tmp_path / f"raw_{mode}_{limit}.txt")
+            ctx.write_raw_qic(ref.taxa, p)
+            assert open(p).read() == g["rawqic"]
+
+
+def test_raw_qic_from_several_shards(golden, tmp_path):
+    g = golden("s16x300_missing_poly")
+    _, ref, flat = load_input(g)
+    ctxs = []
+    for k in range(3):
+        c = Context(ref.n_taxa, 2, shard_index=k, shard_count=3)
+        c.set_reference(ref)
+        c.add_trees(flat)
+        c.count()
+        ctxs.append(c)
+    p = str(tmp_path / "raw.txt")
+    Context.write_raw_qic_shards(ctxs, ref.taxa, p)
+    assert open(p).read() == g["rawqic"]
+    from quartetscores_b200 import QSError
+    with pytest.raises(QSError):
+        ctxs[1].write_raw_qic(ref.taxa, p)                 # one shard alone cannot write the file
+    for c in ctxs:
+        c.close()

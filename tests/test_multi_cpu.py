@@ -57,7 +57,10 @@ def _ref_tables(ref):
     for i in range(1, N):
         depth[i] = depth[parent[i]] + 1
     is_inner = [ref.leaf_lookup_id[i] < 0 for i in range(N)]
-    inner_nodes = [i for i in range(N) if is_inner[i]]
+    with Context(ref.n_taxa, 2, device=QS_DEVICE_NONE) as host:          # the library's order of inner nodes (include/qscuda.h)
+        host.set_reference(ref)
+        inner_nodes = [int(v) for v in host.inner_nodes()]
+    assert sorted(inner_nodes) == [i for i in range(N) if is_inner[i]]
     inner_index = {v: k for k, v in enumerate(inner_nodes)}
     leaf_node = {int(ref.leaf_lookup_id[i]): i for i in range(N) if not is_inner[i]}
 
