@@ -163,9 +163,10 @@ int qs_shard_range(const qs_ctx* ctx, uint64_t* rank_begin, uint64_t* rank_end);
 int qs_shard_bounds(int n_taxa, int shard_index, int shard_count, int* s3_begin, int* s3_end, uint64_t* rank_begin, uint64_t* rank_end);
 
 /* Diagnostics of the counting kernel's host-built task table for the quartets with s3 in [s3_begin, s3_end)
- * (pure host function, no context, no GPU).  stats[12] = {X tasks, Y tasks, XO items, XD items, Y items,
+ * (pure host function, no context, no GPU).  stats[15] = {X tasks, Y tasks, XO items, XD items, Y items,
  * XO item slots, XD item slots, Y item slots, staged rows summed over tasks, max rows of a task,
- * self-check violations (must be 0: tasks tile each enumeration, every item's rows are staged), quartets}. */
+ * self-check violations (must be 0: tasks tile each enumeration, every item's rows are staged), quartets,
+ * XR items, XR item slots, compares issued by role X per tree (2 x quartets of them are useful)}. */
 int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats);
 
 /* Parity hook for the distance kernel: tree t's matrix as n x n uint16 (0xFFFF = taxon missing). */

@@ -97,6 +97,21 @@ __device__ __forceinline__ void step_gt_lt(XCounters& x, const BlockRows& r) {
     }
 }
 
+// the same with G already formed, over the first JM of the 8 "v" taxa (JM < 8: the ragged b-block of role X, count_rows.cuh)
+struct BlockG { __half2 u[4], v[4]; };
+template <int JM>
+__device__ __forceinline__ void step_gt_lt_g(XCounters& x, const BlockG& g) {
+#pragma unroll
+    for (int j = 0; j < JM; ++j) {
+        const __half2 b = (j & 1) ? __high2half2(g.v[j >> 1]) : __low2half2(g.v[j >> 1]);
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            acc_gt(x.gt[j][p], g.u[p], b);
+            acc_lt(x.lt[j][p], g.u[p], b);
+        }
+    }
+}
+
 // G(u) > G(v) only: role Y (pair (b,c) fixed, u = a, v = d: ab|cd, slot 0)
 __device__ __forceinline__ void step_gt(GCounters& y, const BlockRows& r) {
     __half2 u[4], v[4];

@@ -37,12 +37,13 @@
 // uint8 fields per word; all arithmetic is mod 2^32 and every field ends non-negative and in range, so
 // transient carries between fields cancel).
 #pragma once
+#include <type_traits>
 #include "common.cuh"
 #include "count_roles.cuh"
 
 namespace qs {
 
-enum { ITEM_XO = 0, ITEM_XD = 1, ITEM_Y = 2 };
+enum { ITEM_XO = 0, ITEM_XD = 1, ITEM_Y = 2, ITEM_XR = 3 };
 
 struct RowTask {
     int32_t kind;           // ITEM_*
@@ -58,6 +59,7 @@ struct EnumTables {
     const int64_t* PXD;     // [n+1] XD items with c' < c
     const int64_t* PY;      // [n+1] Y items with b' < b
     const int64_t* CD;      // [n+1] d-blocks of role Y over c' < c
+    const int64_t* PXR;     // [n+1] XR items with c' < c
     int xo_diag;            // 1: diagonal blocks are ordinary XO items (ia <= ib) and there are no XD items (large n, where
                             //    XD tasks would be starved of items by the row budget and diagonal blocks are a few % of the work)
 };
@@ -87,6 +89,7 @@ struct CountRowsArgs {
 #ifndef CR_UNROLL_HALVES
 #define CR_UNROLL_HALVES 1
 #endif
+
 constexpr int kUnrollPf = CR_UNROLL_PF, kUnrollHalves = CR_UNROLL_HALVES;
 // CTA shapes of the counting kernel (template parameters THREADS, CTAS per SM), always 16 warps per SM:
 //   512 x 1 : one CTA owns the SM's whole staging ring — best while a task's rows are a large part of the matrix (n <= 112)
@@ -100,9 +103,18 @@ constexpr int CR_SMEM_HEADER = 128 + 4 * 4096;     // barriers + done counters +
 
 // ---- the enumerations (shared by the host task builder and the kernel) ---------------------------------------
 __host__ __device__ __forceinline__ int cr_nxd(int c, int xo_diag) { return (!xo_diag && c >= 2) ? ((c - 2) >> 3) + 1 : 0; }   // blocks with two taxa below c
-__host__ __device__ __forceinline__ int cr_nxo(int c, int xo_diag) {                                                          // b-blocks below c, ia < ib
-    const int nb = (c + 7) >> 3;
-    return nb * (nb - 1) / 2 + (xo_diag ? cr_nxd(c, 0) : 0);                                                                   // (+ the diagonal blocks)
+// b-blocks below c: nfull of them hold 8 taxa below c; when c is not a multiple of 8 one more, ragged, holds c & 7.  XO items pair
+// an a-block with a FULL b-block (ia < ib; ia <= ib when the diagonal blocks are XO items too); the ragged b-block's items are a kind
+// of their own, XR, whose tree loop only runs over the c & 7 valid b — with them inside XO every (c,d) paid a whole block row
+// for a partly empty one: 15 % of all compares at n = 100 (enumeration efficiency 0.85 -> 0.97).
+__host__ __device__ __forceinline__ int cr_nfull(int c) { return c >> 3; }
+__host__ __device__ __forceinline__ int cr_nxo(int c, int xo_diag) {
+    const int nf = cr_nfull(c);
+    return nf * (nf - 1) / 2 + ((xo_diag && c >= 2) ? nf : 0);
+}
+__host__ __device__ __forceinline__ int cr_nxr(int c, int xo_diag) {
+    if ((c & 7) == 0 || c < 2) return 0;
+    return cr_nfull(c) + ((xo_diag && (c & 7) >= 2) ? 1 : 0);          // ia = 0 .. nfull-1 (+ the ragged diagonal block, if it holds two taxa)
 }
 __host__ __device__ __forceinline__ int cr_dlo(int c, int d_begin) { return c + 1 > d_begin ? c + 1 : d_begin; }
 __host__ __device__ __forceinline__ int cr_ndb(int c, int d_begin, int d_end) {                                    // d-blocks (of 8) above c
@@ -121,7 +133,7 @@ __host__ __device__ __forceinline__ int cr_ub(const int64_t* P, int lo, int hi, 
 __host__ __device__ __forceinline__ void cr_decode_x(const int64_t* P, int kind, int xo_diag, int64_t e, int n, int d_begin, int& c, int& d, int& j) {
     c = cr_ub(P, 0, n, e);
     const int64_t r = e - P[c];
-    const int cnt = kind == ITEM_XO ? cr_nxo(c, xo_diag) : cr_nxd(c, xo_diag);
+    const int cnt = kind == ITEM_XO ? cr_nxo(c, xo_diag) : kind == ITEM_XR ? cr_nxr(c, xo_diag) : cr_nxd(c, xo_diag);
     d = cr_dlo(c, d_begin) + (int)(r / cnt);
     j = (int)(r % cnt);
 }
@@ -290,29 +302,53 @@ __global__ void __launch_bounds__(THREADS, cr_ctas_per_sm(THREADS)) qs_count_row
         const bool cls_a = (cls == 0);
         const uint32_t rb = a.row_bytes;
 
-        if (T.kind == ITEM_XO) {
+        if (T.kind == ITEM_XO || T.kind == ITEM_XR) {
+            const bool ragged = T.kind == ITEM_XR;
             const bool valid = tid < T.ne;
             int c = 2, d = 3, j = 0;
-            if (valid) cr_decode_x(a.E.PXO, ITEM_XO, a.E.xo_diag, T.e0 + tid, a.n, a.d_begin, c, d, j);
+            if (valid) cr_decode_x(ragged ? a.E.PXR : a.E.PXO, T.kind, a.E.xo_diag, T.e0 + tid, a.n, a.d_begin, c, d, j);
             int ib = 1, ia = 0;
             if (valid) {
-                const int noff = ((c + 7) >> 3) * (((c + 7) >> 3) - 1) / 2;      // off-diagonal blocks first: j = ib(ib-1)/2 + ia, ia < ib
-                if (j < noff) {
-                    ib = (int)((1.f + sqrtf(1.f + 8.f * (float)j)) * 0.5f);
-                    while (ib * (ib - 1) / 2 > j) --ib;
-                    while ((ib + 1) * ib / 2 <= j) ++ib;
-                    ia = j - ib * (ib - 1) / 2;
-                } else ia = ib = j - noff;                                        // xo_diag: then the diagonal blocks
+                const int nf = cr_nfull(c);
+                if (ragged) { ib = nf; ia = j; }                                  // ragged b-block nf: a-blocks 0 .. nf-1, then (xo_diag) the diagonal block
+                else {
+                    const int noff = nf * (nf - 1) / 2;                           // off-diagonal blocks first: j = ib(ib-1)/2 + ia, ia < ib
+                    if (j < noff) {
+                        ib = (int)((1.f + sqrtf(1.f + 8.f * (float)j)) * 0.5f);
+                        while (ib * (ib - 1) / 2 > j) --ib;
+                        while ((ib + 1) * ib / 2 <= j) ++ib;
+                        ia = j - ib * (ib - 1) / 2;
+                    } else ia = ib = j - noff;                                    // xo_diag: then the diagonal blocks
+                }
             }
+            // valid b of the b-block: 8, or c & 7 in the ragged one; the tree loop runs over the largest count in the warp
+            // (a task's items nearly always share c, so it is the same for all lanes)
+            int jmax = 8;
+            if (ragged) jmax = __reduce_max_sync(0xffffffffu, valid ? (c & 7) : 1);
             // pair (p,q) = (c,d)
             const uint32_t rp = valid ? cr_row_off(T, c, rb) : 0u, rq = valid ? cr_row_off(T, d, rb) : 0u;
             const uint32_t oPu = rp + ia * 16u, oQu = rq + ia * 16u, oPv = rp + ib * 16u, oQv = rq + ib * 16u;
             XCounters x; zero(x);
-            stream_rows<THREADS>(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
-                stage_pf(base, nt, slot,
-                         [&](const unsigned char* s) { return BlockRows{lds128(s, oPu), lds128(s, oQu), lds128(s, oPv), lds128(s, oQv)}; },
-                         [&](const BlockRows& r) { step_gt_lt(x, r); });
-            });
+            auto run = [&](auto jm) {
+                constexpr int JM = decltype(jm)::value;
+                stream_rows<THREADS>(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
+                    // the prefetched operand set of a tree is G itself (8 registers), not the four raw row segments (16): -2.5 % at
+                    // cfg2, -5 % at n = 200 (profiles/r02_e_count_variants.txt)
+                    stage_pf(base, nt, slot,
+                             [&](const unsigned char* s) { BlockG g; sub4(g.u, lds128(s, oQu), lds128(s, oPu)); sub4(g.v, lds128(s, oQv), lds128(s, oPv)); return g; },
+                             [&](const BlockG& g) { step_gt_lt_g<JM>(x, g); });
+                });
+            };
+            switch (jmax) {
+                case 1: run(std::integral_constant<int, 1>()); break;
+                case 2: run(std::integral_constant<int, 2>()); break;
+                case 3: run(std::integral_constant<int, 3>()); break;
+                case 4: run(std::integral_constant<int, 4>()); break;
+                case 5: run(std::integral_constant<int, 5>()); break;
+                case 6: run(std::integral_constant<int, 6>()); break;
+                case 7: run(std::integral_constant<int, 7>()); break;
+                default: run(std::integral_constant<int, 8>()); break;
+            }
             if (valid) {
                 const uint64_t rcd = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
 #pragma unroll

@@ -25,8 +25,9 @@
 //   * The pair key (u,v) of a quartet has one end implied by (c,d), so the CTA accumulates in shared memory, indexed by ONE node:
 //       key (x, r)   r = lca(c,d)                                   -> accR[x]   x = lca(a,b) or lca(b,c)
 //       key (p, q)   p = lca(a,b) below q = lca(b,c)                -> accP[p]   (q is the ancestor of p that joins c)
-//       key (q, p)   p above q, both ancestors of c deeper than r   -> accQ[depth(q)-dr-1][depth(p)-dr-1]  (32 levels; deeper
-//                                                                      ones go straight to global memory)
+//       key (q, p)   p above q, both ancestors of c deeper than r   -> accQ[depth(q)-dr-1][depth(p)-dr-1]  (as many levels as the
+//                                                                      reference tree is deep, up to 128; deeper ones go
+//                                                                      straight to global memory)
 //     Inner nodes are numbered by their first gap in the planar leaf order (qscuda.cu build_reference), so every index the
 //     CTA of (c,d) touches is < c and only c entries are zeroed and flushed: one global atomic per touched key and CTA
 //     (~n^3 in total) instead of one per run of equal keys (~0.4 C(n,4)).
@@ -50,7 +51,7 @@ constexpr int QS_TRIPLE_BITS = 21;                             // three counts p
 struct ScoreArgs {
     const void* table;               // CINT [(rank - rank_base)][3]
     uint64_t rank_base;
-    const uint16_t* lca;             // [n][n] inner index of lca(leaf x, leaf y)
+    const uint32_t* lcapd;           // [n][n] inner index of lca(leaf x, leaf y) | its depth << 16 (one load instead of two dependent ones)
     const uint16_t* idepth;          // [I] depth of an inner node (by inner index)
     const uint32_t* run_off;         // [n+1] row b of lca[][] restricted to a < b, run-length encoded: runs run_off[b] .. run_off[b+1]
     const uint32_t* run_end;         //   exclusive end (in a) of the run
@@ -69,6 +70,7 @@ struct ScoreArgs {
     int count_scale;                 // 1 or 2
     unsigned long long cint_mask;
     int bifurcating;                 // argument order of the stored triple (see ordered_triple)
+    int q4_levels;                   // levels of accQ (ancestors of c below r it covers), chosen by the host from the reference tree's depth
 };
 
 __device__ __forceinline__ unsigned long long pack_triple(unsigned long long q1, unsigned long long q2, unsigned long long q3) {
@@ -136,6 +138,15 @@ __device__ __forceinline__ float dev_log_score_f32(unsigned q1, unsigned q2, uns
     if (q1 < max(q2, q3)) qic = -qic;
     return s == 0 ? 0.f : qic;
 }
+// Triples with at most one non-zero count score exactly +1 / -1 / 0 (x * rcp(x) is not exactly 1 in fp32, so the estimate
+// would say 0.99999994): the estimate is replaced by the exact value and compared without the error margin.  Unanimous
+// quartets are the bulk of a well-supported tree; with the margin every one of them would tie with its pair's minimum of 1
+// and take the exact path (measured: 11 % of all quartets, profiles/r02_d_scan_n500_ncu_full.txt).
+__device__ __forceinline__ bool score_known_exactly(unsigned q1, unsigned q2, unsigned q3, float& est) {
+    const bool z1 = q1 == 0, z2 = q2 == 0, z3 = q3 == 0;
+    if ((int)z1 + (int)z2 + (int)z3 >= 2) { est = (z2 && z3) ? (z1 ? 0.f : 1.f) : -1.f; return true; }
+    return false;
+}
 
 // (q1,q2,q3) in the order the reference passes them to log_score, from the table slots (c0,c1,c2) of a sorted quartet whose
 // reference topology is slot `rslot` (0 or 2): processNodePair (ref, S1S3|S2S4, S1S4|S2S3) for a bifurcating reference
@@ -151,18 +162,17 @@ __device__ __forceinline__ void ordered_triple(int rslot, int bifurcating, unsig
 // ---- cold path: one quartet that may be the new minimum of its pair ---------------------------------------------------
 // Evaluate it in fp64 and publish it if it beats the pair's exact minimum.  Protocol on (pair_score, pair_best): lower
 // pair_score first (atomicMin, strict), then install the triple with a CAS loop that gives up as soon as pair_score shows a
-// better one — at the end pair_score[key] is the minimum and pair_best[key] a triple that attains it.  `bound` / `last_t` are
-// the CTA's shared-memory copies for the slot (a conservative fp32 bound of the minimum and the triple that set it): they only
-// filter, races on them are benign.
+// better one — at the end pair_score[key] is the minimum and pair_best[key] a triple that attains it.  `bound` is the CTA's
+// shared-memory copy for the slot (a conservative fp32 bound of the minimum): it only filters, races on it are benign.
 __device__ __noinline__ void scan_candidate(unsigned long long q1, unsigned long long q2, unsigned long long q3, long long key, long long* pair_best,
-                                            long long* pair_score, int* bound, unsigned long long* last_t) {
+                                            long long* pair_score, int* bound) {
     const unsigned long long t = pack_triple(q1, q2, q3);
-    if (last_t && *reinterpret_cast<volatile unsigned long long*>(last_t) == t) return;      // the very counts that hold the slot's minimum
-    const long long mine = double_to_ordered(dev_log_score(q1, q2, q3));
     const long long cur = *reinterpret_cast<volatile long long*>(pair_score + key);
-    if (bound) atomicMin(bound, float_to_ordered(__double2float_ru(ordered_to_double(min(cur, mine)))));
+    if (bound && cur != QS_I64_NONE) atomicMin(bound, float_to_ordered(__double2float_ru(ordered_to_double(cur))));
+    if (*reinterpret_cast<volatile unsigned long long*>(pair_best + key) == t) return;           // the very counts that hold the pair's minimum
+    const long long mine = double_to_ordered(dev_log_score(q1, q2, q3));
     if (!(mine < cur)) return;
-    if (last_t) *reinterpret_cast<volatile unsigned long long*>(last_t) = t;
+    if (bound) atomicMin(bound, float_to_ordered(__double2float_ru(ordered_to_double(mine))));
     if (atomicMin(pair_score + key, mine) <= mine) return;       // somebody holds an equal or better score
     unsigned long long* pb = reinterpret_cast<unsigned long long*>(pair_best + key);
     unsigned long long old = *reinterpret_cast<volatile unsigned long long*>(pb);
@@ -175,13 +185,16 @@ __device__ __noinline__ void scan_candidate(unsigned long long q1, unsigned long
 }
 
 // ---- accumulators of one CTA ------------------------------------------------------------------------------------------
-constexpr int QS_Q4_LEVELS = 32;                                 // accQ covers ancestors of c up to 32 levels below r
-constexpr int QS_Q4_SLOTS = QS_Q4_LEVELS * (QS_Q4_LEVELS - 1) / 2;
+constexpr int QS_Q4_MAX_LEVELS = 128;                            // accQ covers ancestors of c up to q4_levels <= 128 levels below r
+__host__ __device__ __forceinline__ int q4_slots(int levels) { return levels * (levels - 1) / 2; }
 constexpr int QS_SCAN_STEPS = 4;                                 // entries per thread and staged chunk
 __host__ __device__ constexpr int scan_stages(int threads) { return threads >= 1024 ? 2 : 3; }
 __host__ __device__ constexpr uint32_t scan_chunk_bytes(int threads) { return (uint32_t)threads * QS_SCAN_STEPS * 6u; }
-// accumulator slots: accR [0,n), accP [n,2n), accQ [2n, 2n+496).  Per slot: last_t u64 | lo[3] u32 | hi[3] u32 | bound int; then pq [n] u16
-__host__ __device__ __forceinline__ size_t scan_acc_bytes(int n) { return (size_t)(2 * n + QS_Q4_SLOTS) * 36 + (size_t)((n + 7) / 8 * 8) * 2 + 64; }
+// accumulator slots: accR [0,n), accP [n,2n), accQ [2n, 2n + q4_slots).  Per slot: lo[3] u32 | (carry builds: hi[3] u32) | bound int;
+// then pq [n] u16 and anc [levels] int
+__host__ __device__ __forceinline__ size_t scan_acc_bytes(int n, int levels, bool carry) {
+    return (size_t)(2 * n + q4_slots(levels)) * (carry ? 28 : 16) + (size_t)((n + 7) / 8 * 8) * 2 + (size_t)levels * 4 + 64;
+}
 __host__ __device__ __forceinline__ size_t scan_ring_bytes(int threads, int cint_bytes) {
     return 128 + (cint_bytes == 2 ? (size_t)scan_stages(threads) * scan_chunk_bytes(threads) : 0);
 }
@@ -215,23 +228,22 @@ __device__ __forceinline__ int bound_from_score(long long sc) {
 template <typename CINT, int THREADS, bool SMEM_ACC, bool CARRY>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_kernel(const ScoreArgs a) {
     extern __shared__ __align__(128) unsigned char sm_scan[];
-    __shared__ int s_item;
-    __shared__ int s_anc[QS_Q4_LEVELS];
+    __shared__ int s_item, s_levels;
     constexpr bool RING = sizeof(CINT) == 2;
     constexpr int K = QS_SCAN_STEPS, STAGES = scan_stages(THREADS), CHUNK = THREADS * K, WARPS = THREADS / 32;
     constexpr uint32_t CHUNK_BYTES = scan_chunk_bytes(THREADS);
-    const int tid = threadIdx.x, n = a.n;
-    const int n_acc = 2 * n + QS_Q4_SLOTS;
+    const int tid = threadIdx.x, n = a.n, LV = a.q4_levels;
+    const int n_acc = 2 * n + q4_slots(LV);
     uint64_t* full = reinterpret_cast<uint64_t*>(sm_scan);            // [STAGES] chunk landed (TMA transaction barrier)
     uint64_t* empty = full + 4;                                       // [STAGES] every warp is done with the chunk
     unsigned char* ring = sm_scan + 128;
     // accumulators: shared memory, or (large n) this CTA's region of a.scratch
-    unsigned char* acc_base = SMEM_ACC ? sm_scan + scan_ring_bytes(THREADS, (int)sizeof(CINT)) : reinterpret_cast<unsigned char*>(a.scratch) + (size_t)blockIdx.x * scan_acc_bytes(n);
-    unsigned long long* acc_t = reinterpret_cast<unsigned long long*>(acc_base);                  // [n_acc] triple that set the slot's bound
-    uint32_t* acc_lo = reinterpret_cast<uint32_t*>(acc_base + (size_t)n_acc * 8);                 // [3][n_acc] low words of the sums
-    uint32_t* acc_hi = acc_lo + 3 * (size_t)n_acc;                                                // [3][n_acc] carries
+    unsigned char* acc_base = SMEM_ACC ? sm_scan + scan_ring_bytes(THREADS, (int)sizeof(CINT)) : reinterpret_cast<unsigned char*>(a.scratch) + (size_t)blockIdx.x * scan_acc_bytes(n, LV, CARRY);
+    uint32_t* acc_lo = reinterpret_cast<uint32_t*>(acc_base);                                     // [3][n_acc] low words of the sums
+    uint32_t* acc_hi = acc_lo + (CARRY ? 3 * (size_t)n_acc : 0);                                  // [3][n_acc] carries (carry builds only)
     int* acc_b = reinterpret_cast<int*>(acc_hi + 3 * (size_t)n_acc);                              // [n_acc] fp32 bound of the key's minimum (ordered int)
     uint16_t* acc_pq = reinterpret_cast<uint16_t*>(acc_b + n_acc);                                // [n] q of the accP key (p, q)
+    int* s_anc = reinterpret_cast<int*>(acc_pq + (n + 7) / 8 * 8);                                // [LV] ancestors of leaf c below r
     const int shift = a.count_scale == 2 ? 1 : 0;
     const uint32_t mask32 = (uint32_t)a.cint_mask;                    // (counts are <= m < 2^31 whatever CINT is; the scaled value is masked to CINT)
     const CINT* table = reinterpret_cast<const CINT*>(a.table);
@@ -248,6 +260,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         if (CARRY) { const uint32_t old = atomicAdd(acc_lo + k * n_acc + slot, v); if (old + v < old) atomicAdd(acc_hi + k * n_acc + slot, 1u); }
         else atomicAdd(acc_lo + k * n_acc + slot, v);
     };
+    auto tri_row = [](int x) -> int {                                 // row i of the lower-triangular slot x = i(i-1)/2 + j, j < i
+        int i = (int)((1.f + sqrtf(1.f + 8.f * (float)x)) * 0.5f);
+        while (i * (i - 1) / 2 > x) --i;
+        while ((i + 1) * i / 2 <= x) ++i;
+        return i;
+    };
 
     while (true) {
         __syncthreads();
@@ -257,7 +275,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         if (item >= a.n_items) break;
         int c, d;
         scan_item_decode(item, a.d_begin, a.d_end, c, d);
-        const int r = a.lca[(size_t)c * n + d], dr = a.idepth[r];
+        const uint32_t rd = a.lcapd[(size_t)c * n + d];
+        const int r = (int)(rd & 0xffffu), dr = (int)(rd >> 16);
         // the pair's entries (b,a), a < b < c: L = C(c,2) consecutive table entries from E0, read in 48-byte groups
         const uint64_t E0 = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
         const int L = c * (c - 1) / 2;
@@ -272,34 +291,31 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         };
         if (tid == 0) {
             if (RING) for (int k = 0; k < STAGES && k < n_chunks; ++k) issue(k);     // in flight while the accumulators are prepared
-            for (int x = 0; x < QS_Q4_LEVELS; ++x) s_anc[x] = -1;
-            for (int x = a.leaf_parent[c]; x >= 0; x = a.inner_parent[x]) {          // ancestors of leaf c at depths dr+1 .. dr+32
-                const int dx = a.idepth[x];
-                if (dx <= dr) break;
-                if (dx - dr - 1 < QS_Q4_LEVELS) s_anc[dx - dr - 1] = x;
+            int levels = 0;                                                            // ancestors of leaf c at depths dr+1 .. dr+LV
+            for (int x = a.leaf_parent[c]; x >= 0; x = a.inner_parent[x]) {
+                const int lv = (int)a.idepth[x] - dr - 1;
+                if (lv < 0) break;
+                if (lv < LV) { s_anc[lv] = x; levels = max(levels, lv + 1); }
             }
+            s_levels = levels;                                                         // (unary nodes never are an LCA: their levels are never addressed)
         }
         __syncthreads();
-        // zero what this (c,d) can touch (indices < c of accR / accP, all of accQ) and fetch the keys' current minima as fp32 bounds
+        const int nq4 = q4_slots(s_levels);
+        // zero what this (c,d) can touch (indices < c of accR / accP, the present levels of accQ) and fetch the keys' current minima as fp32 bounds
         for (int x = tid; x < c; x += THREADS) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) { acc_lo[k * n_acc + x] = 0; acc_lo[k * n_acc + n + x] = 0; if (CARRY) { acc_hi[k * n_acc + x] = 0; acc_hi[k * n_acc + n + x] = 0; } }
-            acc_t[x] = QS_TRIPLE_NONE; acc_t[n + x] = QS_TRIPLE_NONE;
             acc_b[x] = x != r ? bound_from_score(a.pair_score[pair_key(x, r)]) : QS_BOUND_NONE;
             int bp = QS_BOUND_NONE;
             const int g = a.inner_gap[x];
-            if (g < c) { const int qq = a.lca[(size_t)g * n + c]; if (qq != x) bp = bound_from_score(a.pair_score[pair_key(x, qq)]); }
+            if (g < c) { const int qq = (int)(a.lcapd[(size_t)g * n + c] & 0xffffu); if (qq != x) bp = bound_from_score(a.pair_score[pair_key(x, qq)]); }
             acc_b[n + x] = bp;
         }
-        for (int x = tid; x < QS_Q4_SLOTS; x += THREADS) {
+        for (int x = tid; x < nq4; x += THREADS) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) { acc_lo[k * n_acc + 2 * n + x] = 0; if (CARRY) acc_hi[k * n_acc + 2 * n + x] = 0; }
-            acc_t[2 * n + x] = QS_TRIPLE_NONE;
-            int i = (int)((1.f + sqrtf(1.f + 8.f * (float)x)) * 0.5f);
-            while (i * (i - 1) / 2 > x) --i;
-            while ((i + 1) * i / 2 <= x) ++i;
-            const int u = s_anc[i], v = s_anc[x - i * (i - 1) / 2];
-            acc_b[2 * n + x] = (u >= 0 && v >= 0) ? bound_from_score(a.pair_score[pair_key(u, v)]) : QS_BOUND_NONE;
+            const int i = tri_row(x);
+            acc_b[2 * n + x] = bound_from_score(a.pair_score[pair_key(s_anc[i], s_anc[x - i * (i - 1) / 2])]);
         }
         __syncthreads();
 
@@ -317,19 +333,30 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
                 while ((b + 1) * b / 2 <= x) ++b;
                 aa = x - b * (b - 1) / 2;
             }
+            // lca(b,c) of the row the entries start in and of the next one (K consecutive entries rarely cross more than one row end)
+            const int bq = min(b, c - 1);
+            const uint32_t qd_a = a.lcapd[(size_t)bq * n + c], qd_b = a.lcapd[(size_t)min(bq + 1, c - 1) * n + c];
             int slot[K], rs[K], ku[K], kv[K], qn[K];
             uint32_t c0[K], c1[K], c2[K];
+            uint32_t w[K * 3 / 2];
+            if (RING) {                                               // the K entries are 6K contiguous bytes, 8-byte aligned (K = 4: three 64-bit loads, conflict-free)
+                const uint2* src = reinterpret_cast<const uint2*>(ring + (size_t)stage * CHUNK_BYTES + (size_t)pos0 * 6);
+#pragma unroll
+                for (int i = 0; i < K * 3 / 4; ++i) { const uint2 v = src[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
+            }
 #pragma unroll
             for (int i = 0; i < K; ++i) {
                 const long long xl = x0 + i;
                 slot[i] = -1; rs[i] = 0; ku[i] = kv[i] = qn[i] = 0; c0[i] = c1[i] = c2[i] = 0;
                 if (xl >= 0 && xl < L) {
-                    const int p = a.lca[(size_t)b * n + aa], q = a.lca[(size_t)b * n + c];
-                    const int dp = a.idepth[p], dq = a.idepth[q];
+                    const uint32_t pd = a.lcapd[(size_t)b * n + aa];
+                    const uint32_t qd = b == bq ? qd_a : b == bq + 1 ? qd_b : a.lcapd[(size_t)b * n + c];
+                    const int p = (int)(pd & 0xffffu), dp = (int)(pd >> 16), q = (int)(qd & 0xffffu), dq = (int)(qd >> 16);
                     uint32_t r0, r1, r2;
-                    if (RING) {
-                        const uint16_t* e = reinterpret_cast<const uint16_t*>(ring + (size_t)stage * CHUNK_BYTES) + (pos0 + i) * 3;
-                        r0 = e[0]; r1 = e[1]; r2 = e[2];
+                    if (RING) {                                       // halfwords 3i, 3i+1, 3i+2 of w[]
+                        r0 = (i & 1) ? w[(3 * i) >> 1] >> 16 : w[(3 * i) >> 1] & 0xffffu;
+                        r1 = (i & 1) ? w[(3 * i + 1) >> 1] & 0xffffu : w[(3 * i + 1) >> 1] >> 16;
+                        r2 = (i & 1) ? w[(3 * i + 2) >> 1] >> 16 : w[(3 * i + 2) >> 1] & 0xffffu;
                     } else { const CINT* e = table + (E0 + (uint64_t)xl) * 3; r0 = (uint32_t)e[0]; r1 = (uint32_t)e[1]; r2 = (uint32_t)e[2]; }
                     c0[i] = (r0 << shift) & mask32; c1[i] = (r1 << shift) & mask32; c2[i] = (r2 << shift) & mask32;
                     const int S0 = dp + dr, S2 = min(dp, min(dq, dr)) + dq;
@@ -341,35 +368,45 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
                         rs[i] = 2;
                         if (dp > dr) {
                             const int lq = dq - dr - 1, lp = dp - dr - 1;
-                            slot[i] = lq < QS_Q4_LEVELS ? 2 * n + lq * (lq - 1) / 2 + lp : -2;     // -2: deeper than accQ reaches -> global memory
+                            slot[i] = lq < LV ? 2 * n + lq * (lq - 1) / 2 + lp : -2;               // -2: deeper than accQ reaches -> global memory
                             ku[i] = q; kv[i] = p;
                         } else { slot[i] = q; ku[i] = q; kv[i] = r; }
                     }                                    // else: unresolved in the reference tree (:559-562), slot stays -1
                     if (++aa == b) { aa = 0; ++b; }
                 }
             }
+            // sums: consecutive entries mostly share their slot (the key changes with lca(a,b), every ~8 entries), so they are
+            // added up in registers and sent to shared memory once per run — per-entry REDs from 32 lanes to 3-4 addresses
+            // serialise in the shared-memory pipe (86 % of its wavefronts were such conflicts, profiles/r02_d_*)
+            uint32_t r1s = 0, r2s = 0, r3s = 0;
 #pragma unroll
             for (int i = 0; i < K; ++i) {
                 if (slot[i] == -1) continue;
                 const uint32_t a1 = rs[i] ? c2[i] : c0[i], a3 = rs[i] ? c0[i] : c2[i];   // (reference topology, crossing, other)
                 if (bif) {
-                    if (slot[i] >= 0) {
-                        add_sum(0, slot[i], a1); add_sum(1, slot[i], c1[i]); add_sum(2, slot[i], a3);
-                        if (slot[i] >= n && slot[i] < 2 * n) acc_pq[slot[i] - n] = (uint16_t)qn[i];
-                    } else {
-                        unsigned long long* ps = a.pair_sums + (size_t)pair_key(ku[i], kv[i]) * 3;
-                        if (a1) atomicAdd(ps, (unsigned long long)a1);
-                        if (c1[i]) atomicAdd(ps + 1, (unsigned long long)c1[i]);
-                        if (a3) atomicAdd(ps + 2, (unsigned long long)a3);
+                    r1s += a1; r2s += c1[i]; r3s += a3;
+                    const bool last = i == K - 1 || slot[i + (i < K - 1 ? 1 : 0)] != slot[i] || (slot[i] == -2 && (ku[i + (i < K - 1 ? 1 : 0)] != ku[i] || kv[i + (i < K - 1 ? 1 : 0)] != kv[i]));
+                    if (last) {
+                        if (slot[i] >= 0) {
+                            add_sum(0, slot[i], r1s); add_sum(1, slot[i], r2s); add_sum(2, slot[i], r3s);
+                            if (slot[i] >= n && slot[i] < 2 * n) acc_pq[slot[i] - n] = (uint16_t)qn[i];
+                        } else {
+                            unsigned long long* ps = a.pair_sums + (size_t)pair_key(ku[i], kv[i]) * 3;
+                            if (r1s) atomicAdd(ps, (unsigned long long)r1s);
+                            if (r2s) atomicAdd(ps + 1, (unsigned long long)r2s);
+                            if (r3s) atomicAdd(ps + 2, (unsigned long long)r3s);
+                        }
+                        r1s = r2s = r3s = 0;
                     }
                 }
                 // LQ-IC: fp32 estimate against the slot's bound; the rare quartet that may beat it goes to the exact path
-                const float est = dev_log_score_f32(a1, c1[i], a3);
+                float est = dev_log_score_f32(a1, c1[i], a3);
+                const bool exact = score_known_exactly(a1, c1[i], a3, est);
                 const float bound = slot[i] >= 0 ? ordered_to_float(*reinterpret_cast<volatile int*>(acc_b + slot[i])) : INFINITY;
-                if ((est == 1.f ? est : est - QS_EST_EPS) < bound) {
+                if ((exact ? est : est - QS_EST_EPS) < bound) {
                     unsigned long long q1, q2, q3;
                     ordered_triple(rs[i], a.bifurcating, c0[i], c1[i], c2[i], q1, q2, q3);
-                    scan_candidate(q1, q2, q3, pair_key(ku[i], kv[i]), a.pair_best, a.pair_score, slot[i] >= 0 ? acc_b + slot[i] : nullptr, slot[i] >= 0 ? acc_t + slot[i] : nullptr);
+                    scan_candidate(q1, q2, q3, pair_key(ku[i], kv[i]), a.pair_best, a.pair_score, slot[i] >= 0 ? acc_b + slot[i] : nullptr);
                 }
             }
             if (RING) {
@@ -404,13 +441,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
                 if (touched(x)) flush(x, pair_key(x, r));
                 if (touched(n + x)) flush(n + x, pair_key(x, (int)acc_pq[x]));
             }
-            for (int x = tid; x < QS_Q4_SLOTS; x += THREADS) {
-                if (touched(2 * n + x)) {
-                    int i = (int)((1.f + sqrtf(1.f + 8.f * (float)x)) * 0.5f);
-                    while (i * (i - 1) / 2 > x) --i;
-                    while ((i + 1) * i / 2 <= x) ++i;
-                    flush(2 * n + x, pair_key(s_anc[i], s_anc[x - i * (i - 1) / 2]));
-                }
+            for (int x = tid; x < nq4; x += THREADS) {
+                if (touched(2 * n + x)) { const int i = tri_row(x); flush(2 * n + x, pair_key(s_anc[i], s_anc[x - i * (i - 1) / 2])); }
             }
         }
     }

@@ -66,7 +66,7 @@ struct qs_ctx {
 
     bool has_ref = false;
     HostRef ref;
-    uint16_t* d_lca = nullptr;
+    uint32_t* d_lcapd = nullptr;          // [n][n] lca inner index | depth << 16
     uint16_t* d_idepth = nullptr;
     uint32_t *d_run_off = nullptr, *d_run_end = nullptr, *d_run_pd = nullptr;
     int32_t *d_inner_parent = nullptr, *d_leaf_parent = nullptr, *d_inner_gap = nullptr;
@@ -222,7 +222,7 @@ double host_log_score(uint64_t q1, uint64_t q2, uint64_t q3) {
 uint64_t cint_mask(int bytes) { return bytes >= 8 ? ~0ull : ((1ull << (8 * bytes)) - 1); }
 
 void free_all(qs_ctx* c) {
-    cudaFree(c->d_lca); cudaFree(c->d_idepth);
+    cudaFree(c->d_lcapd); cudaFree(c->d_idepth);
     cudaFree(c->d_run_off); cudaFree(c->d_run_end); cudaFree(c->d_run_pd); cudaFree(c->d_inner_parent); cudaFree(c->d_leaf_parent); cudaFree(c->d_inner_gap);
     cudaFree(c->d_inner_node); cudaFree(c->d_node_parent); cudaFree(c->d_node_depth); cudaFree(c->d_node_edge); cudaFree(c->d_node_inner);
     cudaFree(c->d_edge); cudaFree(c->d_edge_out); cudaFree(c->d_scan_scratch); cudaFree(c->d_scan_counter);
@@ -281,9 +281,9 @@ int run_distances(qs_ctx* c) {
 
 // ---- task table of the counting kernel for the quartets with d in [dB, dE) (see kernels/count_rows.cuh) ----
 struct HostEnum {
-    std::vector<int64_t> PXO, PXD, PY, CD;
+    std::vector<int64_t> PXO, PXD, PY, CD, PXR;
     int xo_diag = 0;
-    EnumTables view() const { return EnumTables{PXO.data(), PXD.data(), PY.data(), CD.data(), xo_diag}; }
+    EnumTables view() const { return EnumTables{PXO.data(), PXD.data(), PY.data(), CD.data(), PXR.data(), xo_diag}; }
 };
 
 // separate half-cost tasks for the diagonal blocks pay off while a task's rows can cover most of the matrix
@@ -291,11 +291,12 @@ int use_xo_diag(int n) { return n > 160 ? 1 : 0; }
 
 void build_enum_tables(int n, int dB, int dE, HostEnum& H) {
     H.xo_diag = use_xo_diag(n);
-    H.PXO.assign(n + 1, 0); H.PXD.assign(n + 1, 0); H.PY.assign(n + 1, 0); H.CD.assign(n + 1, 0);
+    H.PXO.assign(n + 1, 0); H.PXD.assign(n + 1, 0); H.PY.assign(n + 1, 0); H.CD.assign(n + 1, 0); H.PXR.assign(n + 1, 0);
     for (int c = 0; c < n; ++c) {
         const int64_t nd = (c >= 2) ? std::max(0, dE - cr_dlo(c, dB)) : 0;
         H.PXO[c + 1] = H.PXO[c] + nd * cr_nxo(c, H.xo_diag);
         H.PXD[c + 1] = H.PXD[c] + nd * cr_nxd(c, H.xo_diag);
+        H.PXR[c + 1] = H.PXR[c] + nd * cr_nxr(c, H.xo_diag);
         H.CD[c + 1] = H.CD[c] + ((c >= 2) ? cr_ndb(c, dB, dE) : 0);
     }
     for (int b = 0; b < n; ++b) {
@@ -313,7 +314,7 @@ void task_row_intervals(const HostEnum& H, int kind, int64_t e0, int ne, int n, 
         cr_decode_y(H.view(), e0, n, dB, p0, q0, t0, t1);
         cr_decode_y(H.view(), e0 + ne - 1, n, dB, p1, q1, t0, t1);
     } else {
-        const int64_t* P = kind == ITEM_XO ? H.PXO.data() : H.PXD.data();
+        const int64_t* P = kind == ITEM_XO ? H.PXO.data() : kind == ITEM_XR ? H.PXR.data() : H.PXD.data();
         cr_decode_x(P, kind, H.xo_diag, e0, n, dB, p0, q0, t0);
         cr_decode_x(P, kind, H.xo_diag, e0 + ne - 1, n, dB, p1, q1, t0);
     }
@@ -364,6 +365,7 @@ void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, int
         }
     };
     emit(xt, ITEM_XO, H.PXO[n], threads);
+    emit(xt, ITEM_XR, H.PXR[n], threads);
     emit(xt, ITEM_XD, H.PXD[n], 2 * threads);
     if (with_y) emit(yt, ITEM_Y, H.PY[n], 2 * threads);
 }
@@ -406,7 +408,7 @@ int upload_plan(qs_ctx* c, const HostPlan& P) {
         if ((r = dev_alloc(c, &c->d_tasks, total + total / 4))) { c->tasks_cap = 0; return r; }
         c->tasks_cap = total + total / 4;
     }
-    if (!c->d_enum && (r = dev_alloc(c, &c->d_enum, (size_t)4 * (c->n + 1)))) return r;
+    if (!c->d_enum && (r = dev_alloc(c, &c->d_enum, (size_t)5 * (c->n + 1)))) return r;
     QS_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!xt.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks, xt.data(), xt.size() * sizeof(RowTask), cudaMemcpyHostToDevice));
     if (!yt.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks + xt.size(), yt.data(), yt.size() * sizeof(RowTask), cudaMemcpyHostToDevice));
@@ -415,6 +417,7 @@ int upload_plan(qs_ctx* c, const HostPlan& P) {
     QS_CUDA(c, cudaMemcpy(c->d_enum + np1, P.H.PXD.data(), np1 * 8, cudaMemcpyHostToDevice));
     QS_CUDA(c, cudaMemcpy(c->d_enum + 2 * np1, P.H.PY.data(), np1 * 8, cudaMemcpyHostToDevice));
     QS_CUDA(c, cudaMemcpy(c->d_enum + 3 * np1, P.H.CD.data(), np1 * 8, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_enum + 4 * np1, P.H.PXR.data(), np1 * 8, cudaMemcpyHostToDevice));
     c->plan_dB = P.dB; c->plan_dE = P.dE; c->plan_with_y = P.with_y; c->plan_threads = P.threads; c->plan_nx = (int)xt.size(); c->plan_ny = (int)yt.size(); c->plan_max_rows = P.max_rows;
     return QS_OK;
 }
@@ -468,7 +471,7 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
     a.D = c->d_D; a.order = c->d_order; a.n_class_a = c->d_nA;
     a.tasks = c->d_tasks; a.n_x = c->plan_nx; a.n_y = c->plan_ny;
     const size_t np1 = (size_t)c->n + 1;
-    a.E = EnumTables{c->d_enum, c->d_enum + np1, c->d_enum + 2 * np1, c->d_enum + 3 * np1, use_xo_diag(c->n)};
+    a.E = EnumTables{c->d_enum, c->d_enum + np1, c->d_enum + 2 * np1, c->d_enum + 3 * np1, c->d_enum + 4 * np1, use_xo_diag(c->n)};
     a.task_counter = c->d_counter; a.table = table; a.cint_bytes = c->cint_bytes; a.rank_base = rb;
     a.n = c->n; a.n_pad = c->n_pad; a.m = (int)c->m; a.d_begin = dB; a.d_end = dE;
     a.row_bytes = (uint32_t)c->n_pad * 2u;
@@ -659,8 +662,8 @@ int clear_pair_arrays(qs_ctx* c) {
 // per-CTA accumulators (36 bytes per slot, 2n + 496 slots) fit twice beside the staging rings, 1024 threads above that; for
 // very wide references (n > ~2,300) the accumulators move to global memory.
 template <typename CINT, int THREADS>
-int launch_scan_t(qs_ctx* c, ScoreArgs& a, bool smem_acc) {
-    const size_t ring = scan_ring_bytes(THREADS, (int)sizeof(CINT)), acc = scan_acc_bytes(c->n);
+int launch_scan_t(qs_ctx* c, ScoreArgs& a, bool smem_acc, bool carry) {
+    const size_t ring = scan_ring_bytes(THREADS, (int)sizeof(CINT)), acc = scan_acc_bytes(c->n, a.q4_levels, carry);
     const size_t smem = ring + (smem_acc ? acc : 0);
     int per_sm = std::max(1, std::min(THREADS <= 512 ? 2 : 1, (int)((size_t)c->smem_optin / (smem + 1024))));
     const int grid = (int)std::max<long long>(1, std::min<long long>(a.n_items, (long long)c->num_sms * per_sm));
@@ -674,9 +677,6 @@ int launch_scan_t(qs_ctx* c, ScoreArgs& a, bool smem_acc) {
         a.scratch = c->d_scan_scratch;
     }
     QS_CUDA(c, cudaMemsetAsync(c->d_scan_counter, 0, sizeof(int), c->stream));
-    // can a 32-bit sum overflow inside one (c,d)?  largest stored count x the C(c,2) quartets of the widest pair
-    const uint64_t max_count = std::min<uint64_t>((uint64_t)c->m * (uint64_t)a.count_scale, a.cint_mask);
-    const bool carry = max_count * binom2((uint64_t)std::max(2, a.d_end - 1)) >= (1ull << 32) || getenv("QS_SCAN_CARRY") != nullptr;      // (env: test hook)
     auto go = [&](auto kernel) -> int {
         QS_CUDA(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kernel<<<grid, THREADS, smem, c->stream>>>(a);
@@ -693,12 +693,18 @@ int launch_scan_t(qs_ctx* c, ScoreArgs& a, bool smem_acc) {
 
 template <typename CINT>
 int launch_scan(qs_ctx* c, ScoreArgs& a) {
-    const size_t acc = scan_acc_bytes(c->n), optin = (size_t)c->smem_optin;
+    // can a 32-bit sum overflow inside one (c,d)?  largest stored count x the C(c,2) quartets of the widest pair
+    const uint64_t max_count = std::min<uint64_t>((uint64_t)c->m * (uint64_t)a.count_scale, a.cint_mask);
+    const bool carry = max_count * binom2((uint64_t)std::max(2, a.d_end - 1)) >= (1ull << 32) || getenv("QS_SCAN_CARRY") != nullptr;      // (env: test hook)
+    const size_t optin = (size_t)c->smem_optin;
     const bool force_global = getenv("QS_SCAN_GLOBAL_ACC") != nullptr;                    // test hook: the large-n path on a small input
-    int threads = (2 * (scan_ring_bytes(512, (int)sizeof(CINT)) + acc + 1024) <= optin) ? 512 : 1024;
+    auto fits = [&](int threads, int copies) { return copies * (scan_ring_bytes(threads, (int)sizeof(CINT)) + scan_acc_bytes(c->n, a.q4_levels, carry) + 1024) <= optin; };
+    // accQ shrinks before the accumulators leave shared memory: quartets deeper than its levels take the global-memory path
+    while (a.q4_levels > 16 && !fits(1024, 1)) a.q4_levels = std::max(16, a.q4_levels / 2);
+    int threads = fits(512, 2) ? 512 : 1024;
     if (const char* env = getenv("QS_SCAN_THREADS")) { const int t = atoi(env); if (t == 512 || t == 1024) threads = t; }    // tuning / test hook
-    if (threads == 512) return launch_scan_t<CINT, 512>(c, a, !force_global && scan_ring_bytes(512, (int)sizeof(CINT)) + acc + 1024 <= optin);
-    return launch_scan_t<CINT, 1024>(c, a, !force_global && scan_ring_bytes(1024, (int)sizeof(CINT)) + acc + 1024 <= optin);
+    if (threads == 512) return launch_scan_t<CINT, 512>(c, a, !force_global && fits(512, 1), carry);
+    return launch_scan_t<CINT, 1024>(c, a, !force_global && fits(1024, 1), carry);
 }
 
 // scan a table holding the quartets with d in [dB, dE) and accumulate into the per-pair partials on the device
@@ -707,7 +713,12 @@ int scan_table(qs_ctx* c, const void* table, int dB, int dE, int count_scale) {
     a.n_items = scan_item_count(dB, dE);
     if (a.n_items == 0) return QS_OK;
     if (a.n_items > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "scan work-item count overflow");
-    a.table = table; a.rank_base = binom4((uint64_t)dB); a.lca = c->d_lca; a.idepth = c->d_idepth;
+    a.table = table; a.rank_base = binom4((uint64_t)dB); a.lcapd = c->d_lcapd; a.idepth = c->d_idepth;
+    // accQ levels: the reference tree's depth (no pair of ancestors of a leaf is further apart), capped by QS_Q4_MAX_LEVELS
+    int max_depth = 2;
+    for (uint16_t dd : c->ref.idepth) max_depth = std::max<int>(max_depth, dd + 1);
+    a.q4_levels = std::min(max_depth, QS_Q4_MAX_LEVELS);
+    if (const char* env = getenv("QS_SCAN_LEVELS")) a.q4_levels = std::max(2, std::min(QS_Q4_MAX_LEVELS, atoi(env)));       // test hook: force the deep (global-memory) path
     a.run_off = c->d_run_off; a.run_end = c->d_run_end; a.run_pd = c->d_run_pd; a.inner_parent = c->d_inner_parent; a.leaf_parent = c->d_leaf_parent; a.inner_gap = c->d_inner_gap;
     a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.pair_score = c->d_pair_score; a.scratch = nullptr; a.work_counter = c->d_scan_counter;
     a.n = c->n; a.I = c->ref.n_inner;
@@ -1103,9 +1114,13 @@ int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int3
     if (r) return r;
     if (ctx->host_only) { ctx->has_ref = true; return QS_OK; }
     const size_t n = ctx->n;
-    if ((r = dev_alloc(ctx, &ctx->d_lca, n * n))) return r;
+    if ((r = dev_alloc(ctx, &ctx->d_lcapd, n * n))) return r;
     if ((r = dev_alloc(ctx, &ctx->d_idepth, (size_t)ctx->ref.n_inner))) return r;
-    QS_CUDA(ctx, cudaMemcpy(ctx->d_lca, ctx->ref.lca.data(), n * n * 2, cudaMemcpyHostToDevice));
+    {
+        std::vector<uint32_t> pd(n * n);
+        for (size_t i = 0; i < n * n; ++i) { const uint16_t pn = ctx->ref.lca[i]; pd[i] = (uint32_t)pn | ((uint32_t)ctx->ref.idepth[pn] << 16); }
+        QS_CUDA(ctx, cudaMemcpy(ctx->d_lcapd, pd.data(), n * n * 4, cudaMemcpyHostToDevice));
+    }
     QS_CUDA(ctx, cudaMemcpy(ctx->d_idepth, ctx->ref.idepth.data(), (size_t)ctx->ref.n_inner * 2, cudaMemcpyHostToDevice));
     {   // run-length encoded LCA rows and the parent arrays of the scan / per-edge reduction kernels (kernels/score.cuh)
         const HostRef& R = ctx->ref;
@@ -1363,9 +1378,9 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
     std::vector<RowTask> xt, yt;
     const int threads = cr_threads_for(n_taxa);
     build_row_tasks(H, n_taxa, dB, dE, max_rows, threads, xt, yt);
-    int64_t items[3] = {0, 0, 0}, slots[3] = {0, 0, 0}, rows = 0, mx = 0, violations = 0, quartets = 0;
-    const int cap[3] = {threads, 2 * threads, 2 * threads};
-    int64_t next_e[3] = {0, 0, 0};
+    int64_t items[4] = {0, 0, 0, 0}, slots[4] = {0, 0, 0, 0}, rows = 0, mx = 0, violations = 0, quartets = 0;
+    const int cap[4] = {threads, 2 * threads, 2 * threads, threads};
+    int64_t next_e[4] = {0, 0, 0, 0};
     auto in_ranges = [](const RowTask& t, int row) {
         for (int k = 0; k < 3; ++k) if (row >= t.rstart[k] && row < t.rstart[k] + t.rcount[k]) return true;
         return false;
@@ -1384,18 +1399,23 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
                     cr_decode_y(H.view(), t.e0 + i, n_taxa, dB, p, q, j, k2);
                     if (!(p >= 1 && p < q && q <= dE - 2 && j < (p + 7) / 8 && k2 * 8 < dE && k2 * 8 + 7 >= cr_dlo(q, dB))) ++violations;
                 } else {
-                    cr_decode_x(t.kind == ITEM_XO ? H.PXO.data() : H.PXD.data(), t.kind, H.xo_diag, t.e0 + i, n_taxa, dB, p, q, j);
-                    if (!(p >= 2 && p < q && q >= dB && q < dE && j < (t.kind == ITEM_XO ? cr_nxo(p, H.xo_diag) : cr_nxd(p, H.xo_diag)))) ++violations;
+                    cr_decode_x(t.kind == ITEM_XO ? H.PXO.data() : t.kind == ITEM_XR ? H.PXR.data() : H.PXD.data(), t.kind, H.xo_diag, t.e0 + i, n_taxa, dB, p, q, j);
+                    if (!(p >= 2 && p < q && q >= dB && q < dE && j < (t.kind == ITEM_XO ? cr_nxo(p, H.xo_diag) : t.kind == ITEM_XR ? cr_nxr(p, H.xo_diag) : cr_nxd(p, H.xo_diag)))) ++violations;
                 }
                 if (!in_ranges(t, p) || !in_ranges(t, q)) ++violations;
             }
         }
-    if (next_e[ITEM_XO] != H.PXO[n_taxa] || next_e[ITEM_XD] != H.PXD[n_taxa] || next_e[ITEM_Y] != H.PY[n_taxa]) ++violations;
+    if (next_e[ITEM_XO] != H.PXO[n_taxa] || next_e[ITEM_XD] != H.PXD[n_taxa] || next_e[ITEM_Y] != H.PY[n_taxa] || next_e[ITEM_XR] != H.PXR[n_taxa]) ++violations;
     quartets = (int64_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB));
     stats[0] = (int64_t)xt.size(); stats[1] = (int64_t)yt.size();
     stats[2] = items[0]; stats[3] = items[1]; stats[4] = items[2];
     stats[5] = slots[0]; stats[6] = slots[1]; stats[7] = slots[2];
     stats[8] = rows; stats[9] = mx; stats[10] = violations; stats[11] = quartets;
+    stats[12] = items[ITEM_XR]; stats[13] = slots[ITEM_XR];
+    // useful compares / issued compares of role X: an XO item issues 128 (8 x 8 quartets x 2 slots), an XD item 64, an XR item 16 per valid b
+    int64_t xr_compares = 0;
+    for (int cc = 2; cc < n_taxa; ++cc) xr_compares += (int64_t)std::max(0, dE - cr_dlo(cc, dB)) * cr_nxr(cc, H.xo_diag) * 16 * (cc & 7);
+    stats[14] = items[ITEM_XO] * 128 + items[ITEM_XD] * 64 + xr_compares;
     return QS_OK;
 }
 
