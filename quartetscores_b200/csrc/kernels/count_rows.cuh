@@ -107,13 +107,16 @@ __host__ __device__ __forceinline__ int cr_nxd(int c, int xo_diag) { return (!xo
 // an a-block with a FULL b-block (ia < ib; ia <= ib when the diagonal blocks are XO items too); the ragged b-block's items are a kind
 // of their own, XR, whose tree loop only runs over the c & 7 valid b — with them inside XO every (c,d) paid a whole block row
 // for a partly empty one: 15 % of all compares at n = 100 (enumeration efficiency 0.85 -> 0.97).
-__host__ __device__ __forceinline__ int cr_nfull(int c) { return c >> 3; }
+#ifndef CR_NO_XR
+#define CR_NO_XR 0              // tuning build: 1 = no XR kind, the ragged b-block is an ordinary XO block again
+#endif
+__host__ __device__ __forceinline__ int cr_nfull(int c) { return CR_NO_XR ? (c + 7) >> 3 : c >> 3; }
 __host__ __device__ __forceinline__ int cr_nxo(int c, int xo_diag) {
     const int nf = cr_nfull(c);
     return nf * (nf - 1) / 2 + ((xo_diag && c >= 2) ? nf : 0);
 }
 __host__ __device__ __forceinline__ int cr_nxr(int c, int xo_diag) {
-    if ((c & 7) == 0 || c < 2) return 0;
+    if (CR_NO_XR || (c & 7) == 0 || c < 2) return 0;
     return cr_nfull(c) + ((xo_diag && (c & 7) >= 2) ? 1 : 0);          // ia = 0 .. nfull-1 (+ the ragged diagonal block, if it holds two taxa)
 }
 __host__ __device__ __forceinline__ int cr_dlo(int c, int d_begin) { return c + 1 > d_begin ? c + 1 : d_begin; }
@@ -293,6 +296,9 @@ __global__ void __launch_bounds__(THREADS, cr_ctas_per_sm(THREADS)) qs_count_row
         const long long id = s_task;
         if (id >= nA_tasks + nB_tasks) break;
         int cls, chunk, base_task, nch, lo, len;
+        // chunk-major: CTAs that run at the same time work on different tasks, i.e. flush into different parts of the table (task-major
+        // order — the chunks of one task side by side — made every flush contend for the same L2 lines: +16 % at cfg2, +38 % at n = 200,
+        // profiles/r02_g_sweep_*.txt); inside a chunk the tasks come in table order, longest kinds first (qscuda.cu build_row_tasks)
         if (id < nA_tasks) { cls = 0; chunk = (int)(id / a.n_x); base_task = (int)(id % a.n_x); nch = chA; lo = 0; len = mA; }
         else { const long long r = id - nA_tasks; cls = 1; chunk = (int)(r / (a.n_x + a.n_y)); base_task = (int)(r % (a.n_x + a.n_y)); nch = chB; lo = mA; len = mB; }
         const int per = (len + nch - 1) / nch;                     // balanced chunks, each <= chunk_trees

@@ -63,7 +63,8 @@ struct ScoreArgs {
     long long* pair_best;            // [I*I] packed triple of the min-QIC quartet, QS_I64_NONE = none
     long long* pair_score;           // [I*I] order-preserving int64 image of the EXACT (device fp64) score of pair_best
     unsigned long long* scratch;     // accumulators in global memory (one region per CTA) when they do not fit shared memory
-    int* work_counter;               // dynamic (c,d) scheduling
+    int* work_counter;               // dynamic item scheduling
+    const int4* items;               // work items (c, d0, d1, -): the pairs (c,d), d0 <= d < d1, share r = lca(c,d); largest first
     long long n_items;
     int n, I;
     int d_begin, d_end;
@@ -199,26 +200,6 @@ __host__ __device__ __forceinline__ size_t scan_ring_bytes(int threads, int cint
     return 128 + (cint_bytes == 2 ? (size_t)scan_stages(threads) * scan_chunk_bytes(threads) : 0);
 }
 
-// work item -> (c, d): items are ordered by c descending (the largest pieces first), d ascending inside a c
-__host__ __device__ __forceinline__ long long scan_item_count(int dB, int dE) {
-    const long long W = dE - dB;
-    return W <= 0 ? 0 : W * (W + 1) / 2 + W * (long long)(dB - 3 > 0 ? dB - 3 : 0);
-}
-__device__ __forceinline__ void scan_item_decode(long long j, int dB, int dE, int& c, int& d) {
-    const long long W = dE - dB, tri = W * (W + 1) / 2;
-    if (j < tri) {
-        long long t = (long long)((sqrt(8.0 * (double)j + 1.0) - 1.0) * 0.5);
-        while (t * (t + 1) / 2 > j) --t;
-        while ((t + 1) * (t + 2) / 2 <= j) ++t;
-        c = dE - 2 - (int)t;
-        d = c + 1 + (int)(j - t * (t + 1) / 2);
-    } else {
-        const long long jj = j - tri;
-        c = dB - 2 - (int)(jj / W);
-        d = dB + (int)(jj % W);
-    }
-}
-
 __device__ __forceinline__ int bound_from_score(long long sc) {
     return sc == QS_I64_NONE ? QS_BOUND_NONE : float_to_ordered(__double2float_ru(ordered_to_double(sc)));
 }
@@ -273,24 +254,34 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         __syncthreads();
         const long long item = s_item;
         if (item >= a.n_items) break;
-        int c, d;
-        scan_item_decode(item, a.d_begin, a.d_end, c, d);
-        const uint32_t rd = a.lcapd[(size_t)c * n + d];
+        // item = (c; d0 <= d < d1) with the same r = lca(c,d) for every d: the keys of its quartets do not depend on d, so the
+        // accumulators are set up and flushed once for the whole run of d (on average n / depth pairs instead of one)
+        const int4 it = a.items[item];
+        const int c = it.x, d0 = it.y, d1 = it.z;
+        const uint32_t rd = a.lcapd[(size_t)c * n + d0];
         const int r = (int)(rd & 0xffffu), dr = (int)(rd >> 16);
-        // the pair's entries (b,a), a < b < c: L = C(c,2) consecutive table entries from E0, read in 48-byte groups
-        const uint64_t E0 = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
-        const int L = c * (c - 1) / 2;
-        const uint64_t G0 = E0 >> 3, G1 = (E0 + (uint64_t)L + 7) >> 3;
-        const int n_chunks = (int)((G1 - G0 + CHUNK / 8 - 1) / (CHUNK / 8));
-        auto issue = [&](int k) {                                // thread 0: chunk k of this item -> its ring stage
-            const uint64_t g = G0 + (uint64_t)k * (CHUNK / 8);
+        const int L = c * (c - 1) / 2;                           // entries (b,a), a < b < c, of one (c,d): consecutive in the table from E0(d)
+        auto geom = [&](int d, uint64_t& E0, uint64_t& G0, int& n_chunks) {       // ... read in 48-byte groups [G0, G1), CHUNK/8 groups per chunk
+            E0 = binom4((uint64_t)d) + binom3((uint64_t)c) - a.rank_base;
+            G0 = E0 >> 3;
+            const uint64_t G1 = (E0 + (uint64_t)L + 7) >> 3;
+            n_chunks = (int)((G1 - G0 + CHUNK / 8 - 1) / (CHUNK / 8));
+        };
+        // thread 0: the next chunk to copy in, in the order the CTA consumes them (d ascending, chunks ascending)
+        int is_d = d0, is_k = 0, is_g = 0;
+        auto issue_next = [&]() {
+            uint64_t E0, G0; int nch;
+            geom(is_d, E0, G0, nch);
+            const uint64_t G1 = (E0 + (uint64_t)L + 7) >> 3, g = G0 + (uint64_t)is_k * (CHUNK / 8);
             const uint32_t bytes = (uint32_t)min((uint64_t)(CHUNK / 8), G1 - g) * 48u;
-            uint64_t* bar = &full[k % STAGES];
+            uint64_t* bar = &full[is_g % STAGES];
             mbar_expect_tx(bar, bytes);
-            bulk_g2s(ring + (size_t)(k % STAGES) * CHUNK_BYTES, tbytes + g * 48, bytes, bar);
+            bulk_g2s(ring + (size_t)(is_g % STAGES) * CHUNK_BYTES, tbytes + g * 48, bytes, bar);
+            ++is_g;
+            if (++is_k == nch) { is_k = 0; ++is_d; }
         };
         if (tid == 0) {
-            if (RING) for (int k = 0; k < STAGES && k < n_chunks; ++k) issue(k);     // in flight while the accumulators are prepared
+            if (RING) for (int k = 0; k < STAGES && is_d < d1; ++k) issue_next();     // in flight while the accumulators are prepared
             int levels = 0;                                                            // ancestors of leaf c at depths dr+1 .. dr+LV
             for (int x = a.leaf_parent[c]; x >= 0; x = a.inner_parent[x]) {
                 const int lv = (int)a.idepth[x] - dr - 1;
@@ -301,7 +292,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         }
         __syncthreads();
         const int nq4 = q4_slots(s_levels);
-        // zero what this (c,d) can touch (indices < c of accR / accP, the present levels of accQ) and fetch the keys' current minima as fp32 bounds
+        // zero what this (c, .) can touch (indices < c of accR / accP, the present levels of accQ) and fetch the keys' current minima as fp32 bounds
         for (int x = tid; x < c; x += THREADS) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) { acc_lo[k * n_acc + x] = 0; acc_lo[k * n_acc + n + x] = 0; if (CARRY) { acc_hi[k * n_acc + x] = 0; acc_hi[k * n_acc + n + x] = 0; } }
@@ -319,8 +310,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         }
         __syncthreads();
 
-        for (int k = 0; k < n_chunks; ++k) {
-            const int stage = k % STAGES;
+        int gk = 0;                                              // chunks consumed so far in this item (ring position)
+        for (int d = d0; d < d1; ++d) {
+        uint64_t E0, G0; int n_chunks;
+        geom(d, E0, G0, n_chunks);
+        for (int k = 0; k < n_chunks; ++k, ++gk) {
+            const int stage = gk % STAGES;
             if (RING) { mbar_wait(&full[stage], (full_phase >> stage) & 1u); full_phase ^= 1u << stage; }
             // this thread's K consecutive entries of the chunk: the loads of the K entries are independent and overlap
             const int pos0 = tid * K;
@@ -335,7 +330,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
             }
             // lca(b,c) of the row the entries start in and of the next one (K consecutive entries rarely cross more than one row end)
             const int bq = min(b, c - 1);
-            const uint32_t qd_a = a.lcapd[(size_t)bq * n + c], qd_b = a.lcapd[(size_t)min(bq + 1, c - 1) * n + c];
+            const uint32_t* lrow = a.lcapd + (uint32_t)bq * (uint32_t)n;                 // (n^2 < 2^32)
+            const uint32_t qd_a = lrow[c], qd_b = a.lcapd[(uint32_t)min(bq + 1, c - 1) * (uint32_t)n + c];
             int slot[K], rs[K], ku[K], kv[K], qn[K];
             uint32_t c0[K], c1[K], c2[K];
             uint32_t w[K * 3 / 2];
@@ -349,8 +345,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
                 const long long xl = x0 + i;
                 slot[i] = -1; rs[i] = 0; ku[i] = kv[i] = qn[i] = 0; c0[i] = c1[i] = c2[i] = 0;
                 if (xl >= 0 && xl < L) {
-                    const uint32_t pd = a.lcapd[(size_t)b * n + aa];
-                    const uint32_t qd = b == bq ? qd_a : b == bq + 1 ? qd_b : a.lcapd[(size_t)b * n + c];
+                    const uint32_t pd = lrow[aa];
+                    const uint32_t qd = b == bq ? qd_a : b == bq + 1 ? qd_b : lrow[c];
                     const int p = (int)(pd & 0xffffu), dp = (int)(pd >> 16), q = (int)(qd & 0xffffu), dq = (int)(qd >> 16);
                     uint32_t r0, r1, r2;
                     if (RING) {                                       // halfwords 3i, 3i+1, 3i+2 of w[]
@@ -372,7 +368,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
                             ku[i] = q; kv[i] = p;
                         } else { slot[i] = q; ku[i] = q; kv[i] = r; }
                     }                                    // else: unresolved in the reference tree (:559-562), slot stays -1
-                    if (++aa == b) { aa = 0; ++b; }
+                    if (++aa == b) { aa = 0; ++b; lrow += n; }
                 }
             }
             // sums: consecutive entries mostly share their slot (the key changes with lca(a,b), every ~8 entries), so they are
@@ -414,12 +410,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
                 // into the stages that are already loaded — no CTA-wide barrier in the loop)
                 __syncwarp();
                 if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
-                if (tid == 0 && k + STAGES < n_chunks) {
-                    mbar_wait(&empty[stage], (empty_phase >> stage) & 1u);
-                    issue(k + STAGES);
+                if (tid == 0) {
+                    if (is_d < d1) { mbar_wait(&empty[stage], (empty_phase >> stage) & 1u); issue_next(); }
+                    empty_phase ^= 1u << stage;                  // (phases of chunks that are not refilled complete too: every chunk gets WARPS arrivals)
                 }
-                if (tid == 0) empty_phase ^= 1u << stage;        // (phases of chunks that are not refilled complete too: every chunk gets WARPS arrivals)
             }
+        }
         }
         __syncthreads();
         // ---- flush the CTA's accumulators: one global atomic per touched key ----

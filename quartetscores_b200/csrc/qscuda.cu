@@ -76,6 +76,10 @@ struct qs_ctx {
     unsigned long long* d_scan_scratch = nullptr;
     size_t scan_scratch_bytes = 0;
     int* d_scan_counter = nullptr;
+    int4* d_scan_items = nullptr;         // work items of the scan for the d-range [scan_dB, scan_dE)
+    size_t scan_items_cap = 0;
+    int64_t scan_n_items = 0;
+    int scan_dB = -1, scan_dE = -1;
 
     // trees
     int64_t m = 0, total_nodes = 0, cap_nodes = 0, cap_trees = 0;
@@ -104,6 +108,9 @@ struct qs_ctx {
     RowTask* d_tasks = nullptr;  // task table of the d-range [plan_dB, plan_dE)
     size_t tasks_cap = 0;
     int plan_dB = -1, plan_dE = -1, plan_with_y = 0, plan_threads = 0, plan_nx = 0, plan_ny = 0, plan_max_rows = 1;
+    std::vector<float> plan_xcost, plan_ycost;
+    int64_t chunk_key[4] = {-1, -1, -1, -1}, chunk_choice = 1;      // cached chunk count for (plan generation, m, |A| hint, CTA slots)
+    int64_t plan_generation = 0;
     int64_t* d_enum = nullptr;   // PXO | PXD | PY | CD prefix tables of the plan
     bool counted = false;
     bool counted_once = false;   // n_class_a holds the class split of an earlier qs_count on this context
@@ -225,7 +232,7 @@ void free_all(qs_ctx* c) {
     cudaFree(c->d_lcapd); cudaFree(c->d_idepth);
     cudaFree(c->d_run_off); cudaFree(c->d_run_end); cudaFree(c->d_run_pd); cudaFree(c->d_inner_parent); cudaFree(c->d_leaf_parent); cudaFree(c->d_inner_gap);
     cudaFree(c->d_inner_node); cudaFree(c->d_node_parent); cudaFree(c->d_node_depth); cudaFree(c->d_node_edge); cudaFree(c->d_node_inner);
-    cudaFree(c->d_edge); cudaFree(c->d_edge_out); cudaFree(c->d_scan_scratch); cudaFree(c->d_scan_counter);
+    cudaFree(c->d_edge); cudaFree(c->d_edge_out); cudaFree(c->d_scan_scratch); cudaFree(c->d_scan_counter); cudaFree(c->d_scan_items);
     cudaFree(c->d_off); cudaFree(c->d_parent); cudaFree(c->d_leaf);
     cudaFree(c->d_D); cudaFree(c->d_flags); cudaFree(c->d_table);
     cudaFree(c->d_class); cudaFree(c->d_order); cudaFree(c->d_nA); cudaFree(c->d_counter);
@@ -364,9 +371,16 @@ void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, int
             e += ne;
         }
     };
+    // longest tasks first (the kernel hands tasks out in this order): full role-X blocks, diagonal blocks (two half items per
+    // thread), then the ragged b-blocks, whose tree loop is shorter
     emit(xt, ITEM_XO, H.PXO[n], threads);
+#ifdef CR_XR_BEFORE_XD
     emit(xt, ITEM_XR, H.PXR[n], threads);
     emit(xt, ITEM_XD, H.PXD[n], 2 * threads);
+#else
+    emit(xt, ITEM_XD, H.PXD[n], 2 * threads);
+    emit(xt, ITEM_XR, H.PXR[n], threads);
+#endif
     if (with_y) emit(yt, ITEM_Y, H.PY[n], 2 * threads);
 }
 
@@ -382,6 +396,7 @@ struct HostPlan {
     int dB = -1, dE = -1, with_y = 0, max_rows = 1, threads = CR_THREADS_BIG;
     HostEnum H;
     std::vector<RowTask> xt, yt;
+    std::vector<float> xcost, ycost;     // per-thread work of a task per tree, in units of a full role-X item (chunk-count choice)
 };
 
 void build_host_plan(int n, int n_pad, int dB, int dE, bool with_y, int threads, HostPlan& P) {
@@ -391,6 +406,21 @@ void build_host_plan(int n, int n_pad, int dB, int dE, bool with_y, int threads,
     P.dB = dB; P.dE = dE; P.with_y = with_y ? 1 : 0; P.threads = threads;
     build_enum_tables(n, dB, dE, P.H);
     build_row_tasks(P.H, n, dB, dE, max_rows, threads, P.xt, P.yt, with_y);
+    // per-thread cost of a task per tree: a thread runs one XO item, two half-cost XD / Y items, or one XR item over the c & 7 valid
+    // taxa of its ragged block (14 % of an item is operand fetch and loop overhead whatever the block holds)
+    P.xcost.clear(); P.ycost.assign(P.yt.size(), 1.f);
+    for (auto& t : P.xt) {
+        float w = 1.f;
+        if (t.kind == ITEM_XR) {
+            int c0, d0, j0, c1, d1, j1;
+            cr_decode_x(P.H.PXR.data(), ITEM_XR, P.H.xo_diag, t.e0, n, dB, c0, d0, j0);
+            cr_decode_x(P.H.PXR.data(), ITEM_XR, P.H.xo_diag, t.e0 + t.ne - 1, n, dB, c1, d1, j1);
+            int jm = 1;
+            for (int cc = c0; cc <= c1; ++cc) jm = std::max(jm, cc & 7);
+            w = 0.14f + 0.86f * (float)jm / 8.f;
+        }
+        P.xcost.push_back(w);
+    }
     int mx = 1;
     for (auto* v : {&P.xt, &P.yt}) for (auto& t : *v) mx = std::max(mx, t.rcount[0] + t.rcount[1] + t.rcount[2]);
     P.max_rows = mx;
@@ -419,6 +449,7 @@ int upload_plan(qs_ctx* c, const HostPlan& P) {
     QS_CUDA(c, cudaMemcpy(c->d_enum + 3 * np1, P.H.CD.data(), np1 * 8, cudaMemcpyHostToDevice));
     QS_CUDA(c, cudaMemcpy(c->d_enum + 4 * np1, P.H.PXR.data(), np1 * 8, cudaMemcpyHostToDevice));
     c->plan_dB = P.dB; c->plan_dE = P.dE; c->plan_with_y = P.with_y; c->plan_threads = P.threads; c->plan_nx = (int)xt.size(); c->plan_ny = (int)yt.size(); c->plan_max_rows = P.max_rows;
+    c->plan_xcost = P.xcost; c->plan_ycost = P.ycost; ++c->plan_generation;
     return QS_OK;
 }
 
@@ -485,24 +516,53 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
     a.max_tps = CR_MAX_TPS; a.max_stages = CR_MAX_STAGES;
     if (const char* env = getenv("QS_MAX_TPS")) a.max_tps = std::max(1, std::min(32, atoi(env)));             // tuning hooks
     if (const char* env = getenv("QS_MAX_STAGES")) a.max_stages = std::max(2, std::min((int)CR_MAX_STAGES, atoi(env)));
-    // tree chunks: <= QS_MAX_CHUNK_TREES = 4096 trees (the chunk's tree ids live in shared memory) and >= 256; among the chunk counts that give the dynamic scheduler
-    // 3..16 tasks per SM pick the smallest one whose last round of tasks is (nearly) the fullest
-    const bool all_a = c->n_class_a == c->m;
-    const int64_t base = std::max<int64_t>(1, (int64_t)a.n_x + (all_a ? 0 : a.n_y));
-    int64_t best_k = 1; double best_eff = -1;
-    for (int64_t k = std::max<int64_t>(1, (c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES); k <= std::max<int64_t>(1, c->m / 256); ++k) {
-        const int64_t slots = (int64_t)c->num_sms * ctas;
-        const int64_t T = base * k, rounds = (T + slots - 1) / slots;
-        if (rounds > 16 && best_eff >= 0) break;
-        double eff = (double)T / (double)(rounds * slots);
-        if (rounds < 3) eff *= 0.7 + rounds * 0.1;                  // too few tasks per SM: uneven task lengths dominate
-        if (eff > best_eff + 0.005) { best_eff = eff; best_k = k; } // fewer chunks (fewer flushes) unless clearly fuller (r01_p_sweep_*)
+    // Tree chunks: a task runs over <= QS_MAX_CHUNK_TREES = 4096 trees (the chunk's tree ids live in shared memory).  Tasks differ in
+    // length (ragged-block tasks are shorter) and there are only a few per SM, so how well the last ones fill the machine decides
+    // several per cent: the chunk count is the one whose greedy schedule — tasks handed out in table order to the first free
+    // CTA, exactly what the kernel's atomic counter does — ends earliest, with ~40 trees' worth of flush and pipeline start per task (measured: 13 us per task at cfg2, profiles/r02_j_variants.txt).
+    // The class split is the previous run's (a hint: it only affects the choice, never the result).
+    const int64_t mA_hint = c->counted_once ? std::min<int64_t>(c->n_class_a, c->m) : 0, mB_hint = c->m - mA_hint;
+    const int64_t k_min = std::max<int64_t>(1, (c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES);
+    int64_t best_k = k_min;
+    const int64_t ck[4] = {c->plan_generation, c->m, mA_hint, (int64_t)c->num_sms * ctas};
+    if (ck[0] == c->chunk_key[0] && ck[1] == c->chunk_key[1] && ck[2] == c->chunk_key[2] && ck[3] == c->chunk_key[3]) best_k = c->chunk_choice;
+    else {                                                            // (host work: done once per plan and class split, not per step)
+        const int slots = c->num_sms * ctas;
+        const size_t n_tasks = c->plan_xcost.size() + (mB_hint > 0 ? c->plan_ycost.size() : 0);
+        double best_t = -1;
+        std::vector<double> heap;
+        for (int64_t k = k_min; k <= std::max<int64_t>(k_min, c->m / 256) && k <= k_min + 24; ++k) {
+            if ((double)n_tasks * (double)k > 4e5) break;            // thousands of tasks per CTA: the tail no longer matters
+            const int64_t ct = std::max<int64_t>(1, (c->m + k - 1) / k);
+            heap.assign(slots, 0.0);                                  // min-heap of the CTAs' finish times
+            auto run = [&](double cost) {
+                std::pop_heap(heap.begin(), heap.end(), std::greater<double>());
+                heap.back() += cost;
+                std::push_heap(heap.begin(), heap.end(), std::greater<double>());
+            };
+            auto run_class = [&](int64_t len, bool with_y_tasks) {    // kernel order: chunk-major, the tasks of a chunk in table order
+                if (len <= 0) return;
+                const int64_t nch = (len + ct - 1) / ct, per = (len + nch - 1) / nch;
+                for (int64_t ch = 0; ch < nch; ++ch) {
+                    const double trees = (double)std::min(per, len - ch * per);
+                    for (float w : c->plan_xcost) run((double)w * trees + 40.0);
+                    if (with_y_tasks) for (float w : c->plan_ycost) run((double)w * trees + 40.0);
+                }
+            };
+            run_class(mA_hint, false);
+            run_class(mB_hint, true);
+            const double t_end = *std::max_element(heap.begin(), heap.end());
+            if (best_t < 0 || t_end < best_t * 0.995) { best_t = t_end; best_k = k; }      // fewer chunks unless clearly earlier
+        }
+        for (int i = 0; i < 4; ++i) c->chunk_key[i] = ck[i];
+        c->chunk_choice = best_k;
     }
     if (const char* env = getenv("QS_CHUNK_COUNT")) {                  // tuning hook: force the number of tree chunks
         const int64_t k = atoll(env);
         if (k >= 1) best_k = std::max<int64_t>(k, (c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES);
     }
     a.chunk_trees = (int)std::min<int64_t>(QS_MAX_CHUNK_TREES, std::max<int64_t>(1, (c->m + best_k - 1) / best_k));
+    if (getenv("QS_DEBUG_PLAN")) fprintf(stderr, "[qscuda] plan d=[%d,%d) n_x=%d n_y=%d chunks=%lld chunk_trees=%d threads=%d mA_hint=%lld\n", dB, dE, a.n_x, a.n_y, (long long)best_k, a.chunk_trees, threads, (long long)mA_hint);
     const size_t smem = CR_SMEM_HEADER + budget;
     if (threads == CR_THREADS_BIG) QS_CUDA(c, cudaFuncSetAttribute(qs_count_rows_kernel<CR_THREADS_BIG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     else QS_CUDA(c, cudaFuncSetAttribute(qs_count_rows_kernel<CR_THREADS_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -707,12 +767,62 @@ int launch_scan(qs_ctx* c, ScoreArgs& a) {
     return launch_scan_t<CINT, 1024>(c, a, !force_global && fits(1024, 1), carry);
 }
 
+// work items of the scan for the d-range [dB, dE): (c; d0 <= d < d1) with lca(c,d) constant over the run of d, cut so that no
+// item exceeds 1/16 of a CTA's share of the work, largest first (the kernel hands them out through an atomic counter)
+int build_scan_items(qs_ctx* c, int dB, int dE) {
+    if (c->scan_dB == dB && c->scan_dE == dE && c->d_scan_items) return QS_OK;
+    const HostRef& R = c->ref;
+    const int n = c->n;
+    struct Item { int cc, d0, d1; double cost; };
+    std::vector<Item> items;
+    double total = 0;
+    for (int cc = 2; cc < dE - 1 + 1 && cc < n - 1; ++cc) {
+        const int dlo = std::max(cc + 1, dB);
+        for (int d = dlo; d < dE;) {
+            const uint16_t r = R.lca[(size_t)cc * n + d];
+            int e = d + 1;
+            while (e < dE && R.lca[(size_t)cc * n + e] == r) ++e;
+            const double cost = (double)cc * (cc - 1) / 2 * (e - d);
+            items.push_back({cc, d, e, cost});
+            total += cost;
+            d = e;
+        }
+    }
+    const double cap = std::max(4096.0, total / ((double)c->num_sms * 2 * 16));
+    std::vector<int4> out;
+    std::vector<std::pair<double, size_t>> order;
+    for (auto& it : items) {
+        const double per_d = it.cost / (it.d1 - it.d0);
+        const int step = (int)std::max(1.0, std::floor(cap / per_d));
+        for (int d = it.d0; d < it.d1; d += step) {
+            const int e = std::min(it.d1, d + step);
+            order.emplace_back(-(per_d * (e - d)), out.size());
+            out.push_back(make_int4(it.cc, d, e, 0));
+        }
+    }
+    std::sort(order.begin(), order.end());
+    std::vector<int4> sorted(out.size());
+    for (size_t i = 0; i < order.size(); ++i) sorted[i] = out[order[i].second];
+    if (sorted.size() > 0x7fffffffull) QS_FAIL(c, QS_E_UNSUPPORTED, "scan work-item count overflow");
+    if (sorted.size() > c->scan_items_cap) {
+        int r = dev_alloc(c, &c->d_scan_items, sorted.size() + sorted.size() / 4 + 1);
+        if (r) { c->scan_items_cap = 0; return r; }
+        c->scan_items_cap = sorted.size() + sorted.size() / 4 + 1;
+    }
+    QS_CUDA(c, cudaStreamSynchronize(c->stream));                      // a running scan may still read the previous list
+    if (!sorted.empty()) QS_CUDA(c, cudaMemcpy(c->d_scan_items, sorted.data(), sorted.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    c->scan_n_items = (int64_t)sorted.size();
+    c->scan_dB = dB; c->scan_dE = dE;
+    return QS_OK;
+}
+
 // scan a table holding the quartets with d in [dB, dE) and accumulate into the per-pair partials on the device
 int scan_table(qs_ctx* c, const void* table, int dB, int dE, int count_scale) {
     ScoreArgs a{};
-    a.n_items = scan_item_count(dB, dE);
+    int r0;
+    if ((r0 = build_scan_items(c, dB, dE))) return r0;
+    a.items = c->d_scan_items; a.n_items = c->scan_n_items;
     if (a.n_items == 0) return QS_OK;
-    if (a.n_items > 0x7fffffffLL) QS_FAIL(c, QS_E_UNSUPPORTED, "scan work-item count overflow");
     a.table = table; a.rank_base = binom4((uint64_t)dB); a.lcapd = c->d_lcapd; a.idepth = c->d_idepth;
     // accQ levels: the reference tree's depth (no pair of ancestors of a leaf is further apart), capped by QS_Q4_MAX_LEVELS
     int max_depth = 2;
@@ -1139,6 +1249,7 @@ int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int3
     for (auto** q : {(void**)&ctx->d_pair_sums, (void**)&ctx->d_pair_best, (void**)&ctx->d_pair_score, (void**)&ctx->d_pair_score_local, (void**)&ctx->d_edge, (void**)&ctx->d_edge_out})
         if (*q) { cudaFree(*q); *q = nullptr; }
     ctx->fused_partials_valid = false; ctx->partials_ready = false;
+    ctx->scan_dB = ctx->scan_dE = -1;
     ctx->has_ref = true;
     return QS_OK;
 }
