@@ -71,7 +71,8 @@ const char* qs_strerror(int code);
 int qs_abi_version(void);
 
 /* Launch all work of this context on the given cudaStream_t (passed as void*; NULL = the context's
- * own stream).  Lets a host framework time the kernels with its own events. */
+ * own non-blocking stream; for the legacy default stream pass cudaStreamLegacy, (void*)1).  Lets a host
+ * framework time the kernels with its own events and order its collectives with them. */
 int qs_set_stream(qs_ctx* ctx, void* cuda_stream);
 
 /* Table-free contexts score while they count, so the count semantics must be known before qs_count:

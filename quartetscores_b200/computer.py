@@ -69,7 +69,13 @@ class Context:
         self.close()
 
     def set_stream(self, cuda_stream_handle: int):
-        self._check(self._lib.qs_set_stream(self._h, C.c_void_p(cuda_stream_handle)), "qs_set_stream")
+        """Run this context's work on the given CUDA stream.  torch's default stream has handle 0, which the C ABI reads as
+        "the context's own stream": it is passed as cudaStreamLegacy (1) instead, so that torch ops and NCCL collectives issued
+        on torch's current stream are ordered with the library's kernels."""
+        self._check(self._lib.qs_set_stream(self._h, C.c_void_p(cuda_stream_handle if cuda_stream_handle else 1)), "qs_set_stream")
+
+    def reset_stream(self):
+        self._check(self._lib.qs_set_stream(self._h, None), "qs_set_stream")
 
     def set_count_scale(self, count_scale: int):
         self._check(self._lib.qs_set_count_scale(self._h, count_scale), "qs_set_count_scale")

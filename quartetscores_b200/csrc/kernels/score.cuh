@@ -191,28 +191,73 @@ __host__ __device__ __forceinline__ int q4_slots(int levels) { return levels * (
 constexpr int QS_SCAN_STEPS = 4;                                 // entries per thread and staged chunk
 __host__ __device__ constexpr int scan_stages(int threads) { return threads >= 1024 ? 2 : 3; }
 __host__ __device__ constexpr uint32_t scan_chunk_bytes(int threads) { return (uint32_t)threads * QS_SCAN_STEPS * 6u; }
-// accumulator slots: accR [0,n), accP [n,2n), accQ [2n, 2n + q4_slots).  Per slot: lo[3] u32 | (carry builds: hi[3] u32) | bound int;
+// accumulator slots: accR [0,n), accP [n,2n), accQ [2n, 2n + q4_slots).  Per slot: lo[3] u32 | (carry builds: hi[3] u32) | bound int | tau int;
 // then pq [n] u16 and anc [levels] int
 __host__ __device__ __forceinline__ size_t scan_acc_bytes(int n, int levels, bool carry) {
-    return (size_t)(2 * n + q4_slots(levels)) * (carry ? 28 : 16) + (size_t)((n + 7) / 8 * 8) * 2 + (size_t)levels * 4 + 64;
+    return (size_t)(2 * n + q4_slots(levels)) * (carry ? 32 : 20) + (size_t)((n + 7) / 8 * 8) * 2 + (size_t)levels * 4 + 64;
 }
-__host__ __device__ __forceinline__ size_t scan_ring_bytes(int threads, int cint_bytes) {
-    return 128 + (cint_bytes == 2 ? (size_t)scan_stages(threads) * scan_chunk_bytes(threads) : 0);
+__host__ __device__ __forceinline__ size_t scan_ring_bytes(int threads, int cint_bytes) {       // barriers | staging ring | tau table
+    return 128 + (cint_bytes == 2 ? (size_t)scan_stages(threads) * scan_chunk_bytes(threads) : 0) + (1024 + 8) * 4;
 }
 
 __device__ __forceinline__ int bound_from_score(long long sc) {
     return sc == QS_I64_NONE ? QS_BOUND_NONE : float_to_ordered(__double2float_ru(ordered_to_double(sc)));
 }
 
-// CARRY: the 32-bit shared-memory sums may overflow inside one (c,d) (max count x C(c,2) >= 2^32, decided by the host):
-// every add then returns the old value and feeds a carry word.  Without it the adds are fire-and-forget REDs.
+// ---- cheap exclusion before the estimate ----------------------------------------------------------------------------------
+// For q1 >= max(q2,q3) the score is smallest when the rest is split evenly: score >= g(p1), p1 = q1/s,
+//   g(p) = 1 + (p ln p + (1-p) ln((1-p)/2)) / ln 3,   increasing on [1/3, 1].
+// Each slot keeps tau = the smallest p1 whose g(p1) reaches the slot's bound (rounded up): a quartet with q1 >= max(q2,q3) and
+// q1 >= tau * s cannot beat the pair's minimum and needs no estimate — most quartets of a pair whose minimum lies below them.
+constexpr int QS_TAU_STEPS = 1024;      // tau is tabulated once per CTA at B = j / 1024 and looked up at the next point above the bound (tau grows with B)
+__device__ __forceinline__ float qs_tau_lookup(const float* tab, float B) {
+    if (!(B > 0.f)) return 0.f;
+    if (!(B < 1.f)) return B > 1.f ? INFINITY : 1.f;
+    return tab[min(QS_TAU_STEPS, (int)(B * (float)QS_TAU_STEPS) + 1)];
+}
+__device__ __noinline__ float qs_tau_of_bound(float B) {
+    if (!(B > 0.f)) return 0.f;                                  // every such quartet scores >= 0 >= B
+    if (!(B < 1.f)) return B > 1.f ? INFINITY : 1.f;             // no minimum yet: never excluded; minimum 1: only unanimous quartets are
+    float lo = 1.f / 3.f, hi = 1.f;
+    for (int it = 0; it < 22; ++it) {
+        const float mid = 0.5f * (lo + hi), rest = 1.f - mid;
+        const float gm = 1.f + (mid * lg2_approx(mid) + rest * lg2_approx(fmaxf(rest * 0.5f, 1e-30f))) * 0.63092975357145743710f;
+        if (gm >= B + 4e-6f) hi = mid; else lo = mid;            // (+4e-6: fp32 evaluation error of g, on the safe side)
+    }
+    return fminf(1.f, hi * (1.f + 2e-6f) + 1e-6f);
+}
+
+// ---- cold path of the scan kernel: a quartet that may hold the new minimum of its pair, or one whose key has no slot ------
+// (u,v) = the key's inner nodes; slot < 0: the key is deeper than accQ reaches and its sums go to global memory directly.
+__device__ __noinline__ void scan_cold(unsigned long long* pair_sums, long long* pair_best, long long* pair_score, int I, int bifurcating, int rslot, uint32_t c0,
+                                       uint32_t c1, uint32_t c2, int u, int v, int* bound, int* tau, const float* tau_tab, bool add_sums) {
+    const long long key = (long long)min(u, v) * I + max(u, v);
+    unsigned long long q1, q2, q3;
+    if (add_sums) {                                              // (reference topology, crossing, other): QuartetScoreComputer.hpp:429-431
+        unsigned long long* ps = pair_sums + (size_t)key * 3;
+        const uint32_t a1 = rslot ? c2 : c0, a3 = rslot ? c0 : c2;
+        if (a1) atomicAdd(ps, (unsigned long long)a1);
+        if (c1) atomicAdd(ps + 1, (unsigned long long)c1);
+        if (a3) atomicAdd(ps + 2, (unsigned long long)a3);
+    }
+    ordered_triple(rslot, bifurcating, c0, c1, c2, q1, q2, q3);
+    const int before = bound ? *reinterpret_cast<volatile int*>(bound) : 0;
+    scan_candidate(q1, q2, q3, key, pair_best, pair_score, bound);
+    if (bound && *reinterpret_cast<volatile int*>(bound) != before)
+        atomicMin(tau, float_to_ordered(qs_tau_lookup(tau_tab, ordered_to_float(*reinterpret_cast<volatile int*>(bound)))));
+}
+
+// CARRY: the 32-bit shared-memory sums may overflow inside one item (max count x C(c,2) x run length >= 2^32, decided by the
+// host): every add then returns the old value and feeds a carry word.  Without it the adds are fire-and-forget REDs.
 template <typename CINT, int THREADS, bool SMEM_ACC, bool CARRY>
 __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_kernel(const ScoreArgs a) {
     extern __shared__ __align__(128) unsigned char sm_scan[];
     __shared__ int s_item, s_levels;
+    __shared__ int s_issue[3];                                        // thread 0's copy-in cursor: next d, next chunk of it, chunks issued
     constexpr bool RING = sizeof(CINT) == 2;
     constexpr int K = QS_SCAN_STEPS, STAGES = scan_stages(THREADS), CHUNK = THREADS * K, WARPS = THREADS / 32;
     constexpr uint32_t CHUNK_BYTES = scan_chunk_bytes(THREADS);
+    static_assert(K == 4, "the entry loop below is written for 4 consecutive entries (24 bytes) per thread");
     const int tid = threadIdx.x, n = a.n, LV = a.q4_levels;
     const int n_acc = 2 * n + q4_slots(LV);
     uint64_t* full = reinterpret_cast<uint64_t*>(sm_scan);            // [STAGES] chunk landed (TMA transaction barrier)
@@ -223,8 +268,10 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
     uint32_t* acc_lo = reinterpret_cast<uint32_t*>(acc_base);                                     // [3][n_acc] low words of the sums
     uint32_t* acc_hi = acc_lo + (CARRY ? 3 * (size_t)n_acc : 0);                                  // [3][n_acc] carries (carry builds only)
     int* acc_b = reinterpret_cast<int*>(acc_hi + 3 * (size_t)n_acc);                              // [n_acc] fp32 bound of the key's minimum (ordered int)
-    uint16_t* acc_pq = reinterpret_cast<uint16_t*>(acc_b + n_acc);                                // [n] q of the accP key (p, q)
+    int* acc_tau = acc_b + n_acc;                                                                 // [n_acc] exclusion threshold of the bound (ordered int of a float >= 0)
+    uint16_t* acc_pq = reinterpret_cast<uint16_t*>(acc_tau + n_acc);                              // [n] q of the accP key (p, q)
     int* s_anc = reinterpret_cast<int*>(acc_pq + (n + 7) / 8 * 8);                                // [LV] ancestors of leaf c below r
+    float* s_tau = reinterpret_cast<float*>(sm_scan + 128 + (RING ? (size_t)STAGES * CHUNK_BYTES : 0));   // [QS_TAU_STEPS + 1] (always shared memory)
     const int shift = a.count_scale == 2 ? 1 : 0;
     const uint32_t mask32 = (uint32_t)a.cint_mask;                    // (counts are <= m < 2^31 whatever CINT is; the scaled value is masked to CINT)
     const CINT* table = reinterpret_cast<const CINT*>(a.table);
@@ -241,12 +288,18 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         if (CARRY) { const uint32_t old = atomicAdd(acc_lo + k * n_acc + slot, v); if (old + v < old) atomicAdd(acc_hi + k * n_acc + slot, 1u); }
         else atomicAdd(acc_lo + k * n_acc + slot, v);
     };
-    auto tri_row = [](int x) -> int {                                 // row i of the lower-triangular slot x = i(i-1)/2 + j, j < i
-        int i = (int)((1.f + sqrtf(1.f + 8.f * (float)x)) * 0.5f);
+    auto tri_row = [](int x) -> int {                                 // row i of the lower-triangular index x = i(i-1)/2 + j, j < i
+        int i = (int)(0.5f + sqrtf(2.f * (float)x + 0.25f));
         while (i * (i - 1) / 2 > x) --i;
         while ((i + 1) * i / 2 <= x) ++i;
         return i;
     };
+    auto set_bound = [&](int slot, long long score) {
+        const int bb = bound_from_score(score);
+        acc_b[slot] = bb;
+        acc_tau[slot] = float_to_ordered(qs_tau_lookup(s_tau, ordered_to_float(bb)));
+    };
+    for (int j = tid; j <= QS_TAU_STEPS; j += THREADS) s_tau[j] = qs_tau_of_bound((float)j / (float)QS_TAU_STEPS);
 
     while (true) {
         __syncthreads();
@@ -258,7 +311,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         // accumulators are set up and flushed once for the whole run of d (on average n / depth pairs instead of one)
         const int4 it = a.items[item];
         const int c = it.x, d0 = it.y, d1 = it.z;
-        const uint32_t rd = a.lcapd[(size_t)c * n + d0];
+        const uint32_t rd = a.lcapd[(uint32_t)c * (uint32_t)n + d0];
         const int r = (int)(rd & 0xffffu), dr = (int)(rd >> 16);
         const int L = c * (c - 1) / 2;                           // entries (b,a), a < b < c, of one (c,d): consecutive in the table from E0(d)
         auto geom = [&](int d, uint64_t& E0, uint64_t& G0, int& n_chunks) {       // ... read in 48-byte groups [G0, G1), CHUNK/8 groups per chunk
@@ -267,9 +320,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
             const uint64_t G1 = (E0 + (uint64_t)L + 7) >> 3;
             n_chunks = (int)((G1 - G0 + CHUNK / 8 - 1) / (CHUNK / 8));
         };
-        // thread 0: the next chunk to copy in, in the order the CTA consumes them (d ascending, chunks ascending)
-        int is_d = d0, is_k = 0, is_g = 0;
+        // thread 0: copy in the next chunk, in the order the CTA consumes them (d ascending, chunks ascending)
         auto issue_next = [&]() {
+            const int is_d = s_issue[0], is_k = s_issue[1], is_g = s_issue[2];
             uint64_t E0, G0; int nch;
             geom(is_d, E0, G0, nch);
             const uint64_t G1 = (E0 + (uint64_t)L + 7) >> 3, g = G0 + (uint64_t)is_k * (CHUNK / 8);
@@ -277,11 +330,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
             uint64_t* bar = &full[is_g % STAGES];
             mbar_expect_tx(bar, bytes);
             bulk_g2s(ring + (size_t)(is_g % STAGES) * CHUNK_BYTES, tbytes + g * 48, bytes, bar);
-            ++is_g;
-            if (++is_k == nch) { is_k = 0; ++is_d; }
+            s_issue[2] = is_g + 1;
+            if (is_k + 1 == nch) { s_issue[1] = 0; s_issue[0] = is_d + 1; } else s_issue[1] = is_k + 1;
         };
         if (tid == 0) {
-            if (RING) for (int k = 0; k < STAGES && is_d < d1; ++k) issue_next();     // in flight while the accumulators are prepared
+            s_issue[0] = d0; s_issue[1] = 0; s_issue[2] = 0;
+            if (RING) for (int k = 0; k < STAGES && s_issue[0] < d1; ++k) issue_next();     // in flight while the accumulators are prepared
             int levels = 0;                                                            // ancestors of leaf c at depths dr+1 .. dr+LV
             for (int x = a.leaf_parent[c]; x >= 0; x = a.inner_parent[x]) {
                 const int lv = (int)a.idepth[x] - dr - 1;
@@ -292,130 +346,124 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         }
         __syncthreads();
         const int nq4 = q4_slots(s_levels);
-        // zero what this (c, .) can touch (indices < c of accR / accP, the present levels of accQ) and fetch the keys' current minima as fp32 bounds
+        // zero what this (c, .) can touch (indices < c of accR / accP, the present levels of accQ) and fetch the keys' current minima
         for (int x = tid; x < c; x += THREADS) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) { acc_lo[k * n_acc + x] = 0; acc_lo[k * n_acc + n + x] = 0; if (CARRY) { acc_hi[k * n_acc + x] = 0; acc_hi[k * n_acc + n + x] = 0; } }
-            acc_b[x] = x != r ? bound_from_score(a.pair_score[pair_key(x, r)]) : QS_BOUND_NONE;
-            int bp = QS_BOUND_NONE;
+            set_bound(x, x != r ? a.pair_score[pair_key(x, r)] : QS_I64_NONE);
+            long long sp = QS_I64_NONE;
             const int g = a.inner_gap[x];
-            if (g < c) { const int qq = (int)(a.lcapd[(size_t)g * n + c] & 0xffffu); if (qq != x) bp = bound_from_score(a.pair_score[pair_key(x, qq)]); }
-            acc_b[n + x] = bp;
+            if (g < c) { const int qq = (int)(a.lcapd[(uint32_t)g * (uint32_t)n + c] & 0xffffu); if (qq != x) sp = a.pair_score[pair_key(x, qq)]; }
+            set_bound(n + x, sp);
         }
         for (int x = tid; x < nq4; x += THREADS) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) { acc_lo[k * n_acc + 2 * n + x] = 0; if (CARRY) acc_hi[k * n_acc + 2 * n + x] = 0; }
             const int i = tri_row(x);
-            acc_b[2 * n + x] = bound_from_score(a.pair_score[pair_key(s_anc[i], s_anc[x - i * (i - 1) / 2])]);
+            set_bound(2 * n + x, a.pair_score[pair_key(s_anc[i], s_anc[x - i * (i - 1) / 2])]);
         }
         __syncthreads();
 
         int gk = 0;                                              // chunks consumed so far in this item (ring position)
         for (int d = d0; d < d1; ++d) {
-        uint64_t E0, G0; int n_chunks;
-        geom(d, E0, G0, n_chunks);
-        for (int k = 0; k < n_chunks; ++k, ++gk) {
-            const int stage = gk % STAGES;
-            if (RING) { mbar_wait(&full[stage], (full_phase >> stage) & 1u); full_phase ^= 1u << stage; }
-            // this thread's K consecutive entries of the chunk: the loads of the K entries are independent and overlap
-            const int pos0 = tid * K;
-            const long long x0 = (long long)((G0 << 3) + (uint64_t)k * CHUNK + pos0) - (long long)E0;
-            int b = 1, aa = 0;
-            if (x0 + K > 0 && x0 < L) {                                                  // row of the first entry in range: C(b,2) <= x < C(b+1,2)
-                const int x = (int)max(x0, 0LL);
-                b = (int)((1.f + sqrtf(1.f + 8.f * (float)x)) * 0.5f);
-                while (b * (b - 1) / 2 > x) --b;
-                while ((b + 1) * b / 2 <= x) ++b;
-                aa = x - b * (b - 1) / 2;
-            }
-            // lca(b,c) of the row the entries start in and of the next one (K consecutive entries rarely cross more than one row end)
-            const int bq = min(b, c - 1);
-            const uint32_t* lrow = a.lcapd + (uint32_t)bq * (uint32_t)n;                 // (n^2 < 2^32)
-            const uint32_t qd_a = lrow[c], qd_b = a.lcapd[(uint32_t)min(bq + 1, c - 1) * (uint32_t)n + c];
-            int slot[K], rs[K], ku[K], kv[K], qn[K];
-            uint32_t c0[K], c1[K], c2[K];
-            uint32_t w[K * 3 / 2];
-            if (RING) {                                               // the K entries are 6K contiguous bytes, 8-byte aligned (K = 4: three 64-bit loads, conflict-free)
-                const uint2* src = reinterpret_cast<const uint2*>(ring + (size_t)stage * CHUNK_BYTES + (size_t)pos0 * 6);
+            uint64_t E0, G0; int n_chunks;
+            geom(d, E0, G0, n_chunks);
+            const int off0 = (int)((long long)(G0 << 3) - (long long)E0) + tid * K;      // my first entry of chunk 0 relative to E0 (> -8)
+            for (int k = 0; k < n_chunks; ++k, ++gk) {
+                const int stage = gk % STAGES;
+                if (RING) { mbar_wait(&full[stage], (full_phase >> stage) & 1u); full_phase ^= 1u << stage; }
+                const int xa = off0 + k * CHUNK;                  // entries xa .. xa+3 of this (c,d); valid ones are in [0, L)
+                if (xa + K > 0 && xa < L) {
+                    // row of the first valid entry: C(b,2) <= x < C(b+1,2)
+                    const int xf = max(xa, 0);
+                    int b = (int)(0.5f + sqrtf(2.f * (float)xf + 0.25f));
+                    while (b * (b - 1) / 2 > xf) --b;
+                    while ((b + 1) * b / 2 <= xf) ++b;
+                    int aa = xf - b * (b - 1) / 2;
+                    const uint32_t* lrow = a.lcapd + (uint32_t)b * (uint32_t)n;
+                    uint32_t w[6];
+                    if (RING) {                                   // 24 contiguous bytes, 8-byte aligned: three 64-bit loads, conflict-free
+                        const uint2* src = reinterpret_cast<const uint2*>(ring + (size_t)stage * CHUNK_BYTES + (size_t)tid * (K * 6));
 #pragma unroll
-                for (int i = 0; i < K * 3 / 4; ++i) { const uint2 v = src[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
-            }
+                        for (int i = 0; i < 3; ++i) { const uint2 v = src[i]; w[2 * i] = v.x; w[2 * i + 1] = v.y; }
+                    }
+                    // per entry: the two lca words (eight independent loads), then the slot; predicated, not branched
+                    uint32_t pd[K], qd[K];
+                    int slot[K];
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-                const long long xl = x0 + i;
-                slot[i] = -1; rs[i] = 0; ku[i] = kv[i] = qn[i] = 0; c0[i] = c1[i] = c2[i] = 0;
-                if (xl >= 0 && xl < L) {
-                    const uint32_t pd = lrow[aa];
-                    const uint32_t qd = b == bq ? qd_a : b == bq + 1 ? qd_b : lrow[c];
-                    const int p = (int)(pd & 0xffffu), dp = (int)(pd >> 16), q = (int)(qd & 0xffffu), dq = (int)(qd >> 16);
-                    uint32_t r0, r1, r2;
-                    if (RING) {                                       // halfwords 3i, 3i+1, 3i+2 of w[]
-                        r0 = (i & 1) ? w[(3 * i) >> 1] >> 16 : w[(3 * i) >> 1] & 0xffffu;
-                        r1 = (i & 1) ? w[(3 * i + 1) >> 1] & 0xffffu : w[(3 * i + 1) >> 1] >> 16;
-                        r2 = (i & 1) ? w[(3 * i + 2) >> 1] >> 16 : w[(3 * i + 2) >> 1] & 0xffffu;
-                    } else { const CINT* e = table + (E0 + (uint64_t)xl) * 3; r0 = (uint32_t)e[0]; r1 = (uint32_t)e[1]; r2 = (uint32_t)e[2]; }
-                    c0[i] = (r0 << shift) & mask32; c1[i] = (r1 << shift) & mask32; c2[i] = (r2 << shift) & mask32;
-                    const int S0 = dp + dr, S2 = min(dp, min(dq, dr)) + dq;
-                    qn[i] = q;
-                    if (S0 > S2) {                       // ab|cd: u = deeper(p,q), v = deeper(q,r)
-                        if (dr > dq) { slot[i] = dp > dq ? p : q; ku[i] = slot[i]; kv[i] = r; }
-                        else { slot[i] = n + p; ku[i] = p; kv[i] = q; }        // (dp > dq here)
-                    } else if (S2 > S0) {                // ad|bc: u = q, v = deeper(p,r)
-                        rs[i] = 2;
-                        if (dp > dr) {
-                            const int lq = dq - dr - 1, lp = dp - dr - 1;
-                            slot[i] = lq < LV ? 2 * n + lq * (lq - 1) / 2 + lp : -2;               // -2: deeper than accQ reaches -> global memory
-                            ku[i] = q; kv[i] = p;
-                        } else { slot[i] = q; ku[i] = q; kv[i] = r; }
-                    }                                    // else: unresolved in the reference tree (:559-562), slot stays -1
-                    if (++aa == b) { aa = 0; ++b; lrow += n; }
-                }
-            }
-            // sums: consecutive entries mostly share their slot (the key changes with lca(a,b), every ~8 entries), so they are
-            // added up in registers and sent to shared memory once per run — per-entry REDs from 32 lanes to 3-4 addresses
-            // serialise in the shared-memory pipe (86 % of its wavefronts were such conflicts, profiles/r02_d_*)
-            uint32_t r1s = 0, r2s = 0, r3s = 0;
+                    for (int i = 0; i < K; ++i) {
+                        const int x = xa + i;
+                        pd[i] = lrow[aa]; qd[i] = lrow[c];
+                        if (x >= 0 && x + 1 < L) { if (++aa == b) { aa = 0; ++b; lrow += n; } }            // next entry's row
+                    }
 #pragma unroll
-            for (int i = 0; i < K; ++i) {
-                if (slot[i] == -1) continue;
-                const uint32_t a1 = rs[i] ? c2[i] : c0[i], a3 = rs[i] ? c0[i] : c2[i];   // (reference topology, crossing, other)
-                if (bif) {
-                    r1s += a1; r2s += c1[i]; r3s += a3;
-                    const bool last = i == K - 1 || slot[i + (i < K - 1 ? 1 : 0)] != slot[i] || (slot[i] == -2 && (ku[i + (i < K - 1 ? 1 : 0)] != ku[i] || kv[i + (i < K - 1 ? 1 : 0)] != kv[i]));
-                    if (last) {
-                        if (slot[i] >= 0) {
-                            add_sum(0, slot[i], r1s); add_sum(1, slot[i], r2s); add_sum(2, slot[i], r3s);
-                            if (slot[i] >= n && slot[i] < 2 * n) acc_pq[slot[i] - n] = (uint16_t)qn[i];
+                    for (int i = 0; i < K; ++i) {
+                        const int x = xa + i;
+                        const int p = (int)(pd[i] & 0xffffu), dp = (int)(pd[i] >> 16), q = (int)(qd[i] & 0xffffu), dq = (int)(qd[i] >> 16);
+                        const int S0 = dp + dr, S2 = min(dp, min(dq, dr)) + dq;
+                        const int lq = dq - dr - 1, lp = dp - dr - 1;
+                        const int s_ab = dr > dq ? (dp > dq ? p : q) : n + p;                               // ab|cd: (deeper(p,q), r) or (p, q)
+                        const int s_ad = dp > dr ? (lq < LV ? 2 * n + lq * (lq - 1) / 2 + lp : -2) : q;     // ad|bc: (q, p) or (q, r)
+                        slot[i] = (x < 0 || x >= L) ? -1 : S0 > S2 ? s_ab : S2 > S0 ? s_ad : -1;            // -1: outside, or unresolved in the reference tree (:559-562)
+                    }
+                    // sums: consecutive entries mostly share their slot (the key changes with lca(a,b), every ~8 entries): added up in
+                    // registers, one set of shared-memory REDs per run (per-entry REDs from 32 lanes to 3-4 addresses serialise)
+                    uint32_t r1s = 0, r2s = 0, r3s = 0;
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+                        if (slot[i] == -1) continue;
+                        uint32_t r0, r1, r2;
+                        if (RING) {                               // halfwords 3i, 3i+1, 3i+2 of w[]
+                            r0 = (i & 1) ? w[(3 * i) >> 1] >> 16 : w[(3 * i) >> 1] & 0xffffu;
+                            r1 = (i & 1) ? w[(3 * i + 1) >> 1] & 0xffffu : w[(3 * i + 1) >> 1] >> 16;
+                            r2 = (i & 1) ? w[(3 * i + 2) >> 1] >> 16 : w[(3 * i + 2) >> 1] & 0xffffu;
                         } else {
-                            unsigned long long* ps = a.pair_sums + (size_t)pair_key(ku[i], kv[i]) * 3;
-                            if (r1s) atomicAdd(ps, (unsigned long long)r1s);
-                            if (r2s) atomicAdd(ps + 1, (unsigned long long)r2s);
-                            if (r3s) atomicAdd(ps + 2, (unsigned long long)r3s);
+                            const CINT* e = table + (E0 + (uint64_t)(xa + i)) * 3;
+                            r0 = (uint32_t)e[0]; r1 = (uint32_t)e[1]; r2 = (uint32_t)e[2];
                         }
-                        r1s = r2s = r3s = 0;
+                        const uint32_t c0 = (r0 << shift) & mask32, c1 = (r1 << shift) & mask32, c2 = (r2 << shift) & mask32;
+                        const int dp = (int)(pd[i] >> 16), dq = (int)(qd[i] >> 16);
+                        const bool rs2 = dp + dr <= min(dp, min(dq, dr)) + dq;                              // not ab|cd, i.e. ad|bc
+                        const uint32_t a1 = rs2 ? c2 : c0, a3 = rs2 ? c0 : c2;                              // (reference topology, crossing, other)
+                        if (slot[i] >= 0) {
+                            if (bif) {
+                                r1s += a1; r2s += c1; r3s += a3;
+                                if (i == K - 1 || slot[i + (i < K - 1 ? 1 : 0)] != slot[i]) {
+                                    add_sum(0, slot[i], r1s); add_sum(1, slot[i], r2s); add_sum(2, slot[i], r3s);
+                                    if (slot[i] >= n && slot[i] < 2 * n) acc_pq[slot[i] - n] = (uint16_t)(qd[i] & 0xffffu);
+                                    r1s = r2s = r3s = 0;
+                                }
+                            }
+                            // LQ-IC.  First the cheap exclusion (tau), then the fp32 estimate against the slot's bound; the rare quartet that may
+                            // beat it is evaluated exactly (scan_cold)
+                            const float tau = ordered_to_float(*reinterpret_cast<volatile int*>(acc_tau + slot[i]));
+                            if (!(a1 != 0 && a1 >= max(c1, a3) && (float)a1 >= tau * (float)(a1 + c1 + a3))) {      // (all-zero counts score 0, not >= g)
+                                float est = dev_log_score_f32(a1, c1, a3);
+                                const bool exact = score_known_exactly(a1, c1, a3, est);
+                                const float bound = ordered_to_float(*reinterpret_cast<volatile int*>(acc_b + slot[i]));
+                                if ((exact ? est : est - QS_EST_EPS) < bound) {
+                                    const int p = (int)(pd[i] & 0xffffu), q = (int)(qd[i] & 0xffffu);
+                                    int u, v;
+                                    if (slot[i] < n) { u = slot[i]; v = r; } else if (slot[i] < 2 * n) { u = p; v = q; } else { u = q; v = p; }
+                                    scan_cold(a.pair_sums, a.pair_best, a.pair_score, a.I, a.bifurcating, rs2 ? 2 : 0, c0, c1, c2, u, v, acc_b + slot[i], acc_tau + slot[i], s_tau, false);
+                                }
+                            }
+                        } else {                                  // slot -2: key (q, p) deeper than accQ reaches: sums and selection in global memory
+                            scan_cold(a.pair_sums, a.pair_best, a.pair_score, a.I, a.bifurcating, 2, c0, c1, c2, (int)(qd[i] & 0xffffu), (int)(pd[i] & 0xffffu), nullptr, nullptr, s_tau, bif);
+                        }
                     }
                 }
-                // LQ-IC: fp32 estimate against the slot's bound; the rare quartet that may beat it goes to the exact path
-                float est = dev_log_score_f32(a1, c1[i], a3);
-                const bool exact = score_known_exactly(a1, c1[i], a3, est);
-                const float bound = slot[i] >= 0 ? ordered_to_float(*reinterpret_cast<volatile int*>(acc_b + slot[i])) : INFINITY;
-                if ((exact ? est : est - QS_EST_EPS) < bound) {
-                    unsigned long long q1, q2, q3;
-                    ordered_triple(rs[i], a.bifurcating, c0[i], c1[i], c2[i], q1, q2, q3);
-                    scan_candidate(q1, q2, q3, pair_key(ku[i], kv[i]), a.pair_best, a.pair_score, slot[i] >= 0 ? acc_b + slot[i] : nullptr);
+                if (RING) {
+                    // hand the stage back: one arrival per warp; thread 0 refills it once every warp has arrived (the other warps run on
+                    // into the stages that are already loaded — no CTA-wide barrier in the loop)
+                    __syncwarp();
+                    if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
+                    if (tid == 0) {
+                        if (s_issue[0] < d1) { mbar_wait(&empty[stage], (empty_phase >> stage) & 1u); issue_next(); }
+                        empty_phase ^= 1u << stage;               // (phases of chunks that are not refilled complete too: every chunk gets WARPS arrivals)
+                    }
                 }
             }
-            if (RING) {
-                // hand the stage back: one arrival per warp; thread 0 refills it once every warp has arrived (the other warps run on
-                // into the stages that are already loaded — no CTA-wide barrier in the loop)
-                __syncwarp();
-                if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
-                if (tid == 0) {
-                    if (is_d < d1) { mbar_wait(&empty[stage], (empty_phase >> stage) & 1u); issue_next(); }
-                    empty_phase ^= 1u << stage;                  // (phases of chunks that are not refilled complete too: every chunk gets WARPS arrivals)
-                }
-            }
-        }
         }
         __syncthreads();
         // ---- flush the CTA's accumulators: one global atomic per touched key ----

@@ -761,8 +761,9 @@ int launch_scan(qs_ctx* c, ScoreArgs& a) {
     auto fits = [&](int threads, int copies) { return copies * (scan_ring_bytes(threads, (int)sizeof(CINT)) + scan_acc_bytes(c->n, a.q4_levels, carry) + 1024) <= optin; };
     // accQ shrinks before the accumulators leave shared memory: quartets deeper than its levels take the global-memory path
     while (a.q4_levels > 16 && !fits(1024, 1)) a.q4_levels = std::max(16, a.q4_levels / 2);
-    int threads = fits(512, 2) ? 512 : 1024;
-    if (const char* env = getenv("QS_SCAN_THREADS")) { const int t = atoi(env); if (t == 512 || t == 1024) threads = t; }    // tuning / test hook
+    int threads = fits(384, 2) ? 384 : 1024;          // 384 x 2 CTAs per SM: 85 registers per thread (512 x 2 caps them at 64 and spills: 30 vs 20 ms at n = 500)
+    if (const char* env = getenv("QS_SCAN_THREADS")) { const int t = atoi(env); if (t == 384 || t == 512 || t == 1024) threads = t; }    // tuning / test hook
+    if (threads == 384) return launch_scan_t<CINT, 384>(c, a, !force_global && fits(384, 1), carry);
     if (threads == 512) return launch_scan_t<CINT, 512>(c, a, !force_global && fits(512, 1), carry);
     return launch_scan_t<CINT, 1024>(c, a, !force_global && fits(1024, 1), carry);
 }
