@@ -189,7 +189,7 @@ __device__ __noinline__ void scan_candidate(unsigned long long q1, unsigned long
 constexpr int QS_Q4_MAX_LEVELS = 128;                            // accQ covers ancestors of c up to q4_levels <= 128 levels below r
 __host__ __device__ __forceinline__ int q4_slots(int levels) { return levels * (levels - 1) / 2; }
 constexpr int QS_SCAN_STEPS = 4;                                 // entries per thread and staged chunk
-__host__ __device__ constexpr int scan_stages(int threads) { return threads >= 1024 ? 2 : 3; }
+__host__ __device__ constexpr int scan_stages(int threads) { return threads >= 900 ? 2 : 4; }
 __host__ __device__ constexpr uint32_t scan_chunk_bytes(int threads) { return (uint32_t)threads * QS_SCAN_STEPS * 6u; }
 // accumulator slots: accR [0,n), accP [n,2n), accQ [2n, 2n + q4_slots).  Per slot: lo[3] u32 | (carry builds: hi[3] u32) | bound int | tau int;
 // then pq [n] u16 and anc [levels] int
@@ -250,10 +250,11 @@ __device__ __noinline__ void scan_cold(unsigned long long* pair_sums, long long*
 // CARRY: the 32-bit shared-memory sums may overflow inside one item (max count x C(c,2) x run length >= 2^32, decided by the
 // host): every add then returns the old value and feeds a carry word.  Without it the adds are fire-and-forget REDs.
 template <typename CINT, int THREADS, bool SMEM_ACC, bool CARRY>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_kernel(const ScoreArgs a) {
+__global__ void __launch_bounds__(THREADS + 32, (THREADS <= 512 ? 2 : 1)) qs_scan_kernel(const ScoreArgs a) {
+    // THREADS consumer threads + one producer warp that only copies chunks in (TMA): the refill of a stage never waits for a
+    // consumer to get around to it (with a consumer thread issuing the copies 20 % of all instructions were spins on the full barrier)
     extern __shared__ __align__(128) unsigned char sm_scan[];
     __shared__ int s_item, s_levels;
-    __shared__ int s_issue[3];                                        // thread 0's copy-in cursor: next d, next chunk of it, chunks issued
     constexpr bool RING = sizeof(CINT) == 2;
     constexpr int K = QS_SCAN_STEPS, STAGES = scan_stages(THREADS), CHUNK = THREADS * K, WARPS = THREADS / 32;
     constexpr uint32_t CHUNK_BYTES = scan_chunk_bytes(THREADS);
@@ -277,7 +278,8 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
     const CINT* table = reinterpret_cast<const CINT*>(a.table);
     const unsigned char* tbytes = reinterpret_cast<const unsigned char*>(a.table);
     const bool bif = a.bifurcating != 0;
-    uint32_t full_phase = 0, empty_phase = 0;
+    const bool producer = tid >= THREADS;                              // warp THREADS / 32
+    uint32_t full_phase = 0, empty_phase = 0, stage_used = 0;
     if (RING && tid == 0) {
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], WARPS); }
         fence_mbar_init();
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         acc_b[slot] = bb;
         acc_tau[slot] = float_to_ordered(qs_tau_lookup(s_tau, ordered_to_float(bb)));
     };
-    for (int j = tid; j <= QS_TAU_STEPS; j += THREADS) s_tau[j] = qs_tau_of_bound((float)j / (float)QS_TAU_STEPS);
+    for (int j = tid; j <= QS_TAU_STEPS; j += THREADS + 32) s_tau[j] = qs_tau_of_bound((float)j / (float)QS_TAU_STEPS);
 
     while (true) {
         __syncthreads();
@@ -320,22 +322,24 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
             const uint64_t G1 = (E0 + (uint64_t)L + 7) >> 3;
             n_chunks = (int)((G1 - G0 + CHUNK / 8 - 1) / (CHUNK / 8));
         };
-        // thread 0: copy in the next chunk, in the order the CTA consumes them (d ascending, chunks ascending)
+        // producer warp (one lane): copy the item's chunks in, in the order the consumers take them (d ascending, chunks ascending);
+        // a stage is refilled as soon as every consumer warp has arrived on its empty barrier
+        int pr_d = d0, pr_k = 0, pr_g = 0;                         // producer's cursor: next d, next chunk of it, chunks issued in this item
         auto issue_next = [&]() {
-            const int is_d = s_issue[0], is_k = s_issue[1], is_g = s_issue[2];
             uint64_t E0, G0; int nch;
-            geom(is_d, E0, G0, nch);
-            const uint64_t G1 = (E0 + (uint64_t)L + 7) >> 3, g = G0 + (uint64_t)is_k * (CHUNK / 8);
+            geom(pr_d, E0, G0, nch);
+            const uint64_t G1 = (E0 + (uint64_t)L + 7) >> 3, g = G0 + (uint64_t)pr_k * (CHUNK / 8);
             const uint32_t bytes = (uint32_t)min((uint64_t)(CHUNK / 8), G1 - g) * 48u;
-            uint64_t* bar = &full[is_g % STAGES];
-            mbar_expect_tx(bar, bytes);
-            bulk_g2s(ring + (size_t)(is_g % STAGES) * CHUNK_BYTES, tbytes + g * 48, bytes, bar);
-            s_issue[2] = is_g + 1;
-            if (is_k + 1 == nch) { s_issue[1] = 0; s_issue[0] = is_d + 1; } else s_issue[1] = is_k + 1;
+            const int st = pr_g % STAGES;
+            if ((stage_used >> st) & 1u) { mbar_wait_relaxed(&empty[st], (empty_phase >> st) & 1u); empty_phase ^= 1u << st; }      // its previous chunk is consumed
+            stage_used |= 1u << st;
+            mbar_expect_tx(&full[st], bytes);
+            bulk_g2s(ring + (size_t)st * CHUNK_BYTES, tbytes + g * 48, bytes, &full[st]);
+            ++pr_g;
+            if (++pr_k == nch) { pr_k = 0; ++pr_d; }
         };
+        if (RING && tid == THREADS) for (int k = 0; k < STAGES && pr_d < d1; ++k) issue_next();     // in flight while the accumulators are prepared
         if (tid == 0) {
-            s_issue[0] = d0; s_issue[1] = 0; s_issue[2] = 0;
-            if (RING) for (int k = 0; k < STAGES && s_issue[0] < d1; ++k) issue_next();     // in flight while the accumulators are prepared
             int levels = 0;                                                            // ancestors of leaf c at depths dr+1 .. dr+LV
             for (int x = a.leaf_parent[c]; x >= 0; x = a.inner_parent[x]) {
                 const int lv = (int)a.idepth[x] - dr - 1;
@@ -347,7 +351,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         __syncthreads();
         const int nq4 = q4_slots(s_levels);
         // zero what this (c, .) can touch (indices < c of accR / accP, the present levels of accQ) and fetch the keys' current minima
-        for (int x = tid; x < c; x += THREADS) {
+        for (int x = tid; x < c && !producer; x += THREADS) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) { acc_lo[k * n_acc + x] = 0; acc_lo[k * n_acc + n + x] = 0; if (CARRY) { acc_hi[k * n_acc + x] = 0; acc_hi[k * n_acc + n + x] = 0; } }
             set_bound(x, x != r ? a.pair_score[pair_key(x, r)] : QS_I64_NONE);
@@ -356,7 +360,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
             if (g < c) { const int qq = (int)(a.lcapd[(uint32_t)g * (uint32_t)n + c] & 0xffffu); if (qq != x) sp = a.pair_score[pair_key(x, qq)]; }
             set_bound(n + x, sp);
         }
-        for (int x = tid; x < nq4; x += THREADS) {
+        for (int x = tid; x < nq4 && !producer; x += THREADS) {
 #pragma unroll
             for (int k = 0; k < 3; ++k) { acc_lo[k * n_acc + 2 * n + x] = 0; if (CARRY) acc_hi[k * n_acc + 2 * n + x] = 0; }
             const int i = tri_row(x);
@@ -364,6 +368,9 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
         }
         __syncthreads();
 
+        if (producer) {
+            if (RING && tid == THREADS) while (pr_d < d1) issue_next();
+        } else {
         int gk = 0;                                              // chunks consumed so far in this item (ring position)
         for (int d = d0; d < d1; ++d) {
             uint64_t E0, G0; int n_chunks;
@@ -453,17 +460,12 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
                         }
                     }
                 }
-                if (RING) {
-                    // hand the stage back: one arrival per warp; thread 0 refills it once every warp has arrived (the other warps run on
-                    // into the stages that are already loaded — no CTA-wide barrier in the loop)
+                if (RING) {                                       // hand the stage back: one arrival per consumer warp
                     __syncwarp();
                     if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
-                    if (tid == 0) {
-                        if (s_issue[0] < d1) { mbar_wait(&empty[stage], (empty_phase >> stage) & 1u); issue_next(); }
-                        empty_phase ^= 1u << stage;               // (phases of chunks that are not refilled complete too: every chunk gets WARPS arrivals)
-                    }
                 }
             }
+        }
         }
         __syncthreads();
         // ---- flush the CTA's accumulators: one global atomic per touched key ----
@@ -481,11 +483,11 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 512 ? 2 : 1)) qs_scan_ker
                 if (CARRY) v |= acc_hi[y] | acc_hi[n_acc + y] | acc_hi[2 * n_acc + y];
                 return v != 0;
             };
-            for (int x = tid; x < c; x += THREADS) {
+            for (int x = tid; x < c && !producer; x += THREADS) {
                 if (touched(x)) flush(x, pair_key(x, r));
                 if (touched(n + x)) flush(n + x, pair_key(x, (int)acc_pq[x]));
             }
-            for (int x = tid; x < nq4; x += THREADS) {
+            for (int x = tid; x < nq4 && !producer; x += THREADS) {
                 if (touched(2 * n + x)) { const int i = tri_row(x); flush(2 * n + x, pair_key(s_anc[i], s_anc[x - i * (i - 1) / 2])); }
             }
         }

@@ -739,7 +739,7 @@ int launch_scan_t(qs_ctx* c, ScoreArgs& a, bool smem_acc, bool carry) {
     QS_CUDA(c, cudaMemsetAsync(c->d_scan_counter, 0, sizeof(int), c->stream));
     auto go = [&](auto kernel) -> int {
         QS_CUDA(c, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kernel<<<grid, THREADS, smem, c->stream>>>(a);
+        kernel<<<grid, THREADS + 32, smem, c->stream>>>(a);                       // + the producer warp
         return QS_OK;
     };
     int rr;
@@ -760,12 +760,17 @@ int launch_scan(qs_ctx* c, ScoreArgs& a) {
     const bool force_global = getenv("QS_SCAN_GLOBAL_ACC") != nullptr;                    // test hook: the large-n path on a small input
     auto fits = [&](int threads, int copies) { return copies * (scan_ring_bytes(threads, (int)sizeof(CINT)) + scan_acc_bytes(c->n, a.q4_levels, carry) + 1024) <= optin; };
     // accQ shrinks before the accumulators leave shared memory: quartets deeper than its levels take the global-memory path
-    while (a.q4_levels > 16 && !fits(1024, 1)) a.q4_levels = std::max(16, a.q4_levels / 2);
-    int threads = fits(384, 2) ? 384 : 1024;          // 384 x 2 CTAs per SM: 85 registers per thread (512 x 2 caps them at 64 and spills: 30 vs 20 ms at n = 500)
-    if (const char* env = getenv("QS_SCAN_THREADS")) { const int t = atoi(env); if (t == 384 || t == 512 || t == 1024) threads = t; }    // tuning / test hook
-    if (threads == 384) return launch_scan_t<CINT, 384>(c, a, !force_global && fits(384, 1), carry);
+    // accQ shrinks (down to 40 levels) before the small CTA shape stops fitting twice per SM, and further before the accumulators
+    // leave shared memory: quartets deeper than its levels take the global-memory path
+    const int full_levels = a.q4_levels;
+    while (a.q4_levels > 40 && !fits(352, 2)) a.q4_levels -= 4;
+    if (!fits(352, 2)) a.q4_levels = full_levels;
+    while (a.q4_levels > 16 && !fits(992, 1)) a.q4_levels = std::max(16, a.q4_levels / 2);
+    int threads = fits(352, 2) ? 352 : 1024;          // (352 consumers + the producer warp) x 2 CTAs per SM: 85 registers per thread (512 x 2 caps them at 64 and spills: 30 vs 20 ms at n = 500)
+    if (const char* env = getenv("QS_SCAN_THREADS")) { const int t = atoi(env); if (t == 352 || t == 512 || t == 1024) threads = t; }    // tuning / test hook
+    if (threads == 352) return launch_scan_t<CINT, 352>(c, a, !force_global && fits(352, 1), carry);
     if (threads == 512) return launch_scan_t<CINT, 512>(c, a, !force_global && fits(512, 1), carry);
-    return launch_scan_t<CINT, 1024>(c, a, !force_global && fits(1024, 1), carry);
+    return launch_scan_t<CINT, 992>(c, a, !force_global && fits(992, 1), carry);                  // (992 consumers + the producer warp = 1024 threads)
 }
 
 // work items of the scan for the d-range [dB, dE): (c; d0 <= d < d1) with lca(c,d) constant over the run of d, cut so that no
