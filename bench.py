@@ -307,7 +307,7 @@ def main():
     import numpy as np
     import torch
 
-    from quartetscores_b200 import QS_MODE_TABLE, QS_MODE_TABLE_FREE, Context
+    from quartetscores_b200 import QS_MODE_AUTO, QS_MODE_TABLE_FREE, Context
     from quartetscores_b200.computer import cint_bytes_for
     from quartetscores_b200.multi import shard_bounds
     from quartetscores_b200.multi import score_distributed
@@ -326,7 +326,19 @@ def main():
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # NCCL prints its version banner on stdout when the communicator is created; rank 0's stdout carries ONE JSON line, so
+        # stdout points at stderr until the first collective is through
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     n, m = w["n_taxa"], w["n_trees"]
     nq = comb(n, 4)
@@ -338,9 +350,9 @@ def main():
     h_par = torch.from_numpy(np.ascontiguousarray(flat.parent)).pin_memory()
     h_leaf = torch.from_numpy(np.ascontiguousarray(flat.leaf_lookup_id)).pin_memory()
 
-    _, _, rb0, rb1 = shard_bounds(n, rank, world)
-    table_free = wname == "cfg5" or (rb1 - rb0) * 3 * cint_bytes_for(m) > TABLE_BYTES_LIMIT
-    ctx = Context(n, cint_bytes_for(m), mode=QS_MODE_TABLE_FREE if table_free else QS_MODE_TABLE, device=local_rank, shard_index=rank, shard_count=world)
+    # cfg5 is the reference's -s run: no resident table by request; everything else keeps its shard's table in HBM when it fits
+    # beside the distance matrices and falls back to table-free slabs when it does not (QS_MODE_AUTO: cfg4 on 1-2 GPUs)
+    ctx = Context(n, cint_bytes_for(m), mode=QS_MODE_TABLE_FREE if wname == "cfg5" else QS_MODE_AUTO, device=local_rank, shard_index=rank, shard_count=world)
     if wname == "cfg5":
         ctx.set_count_scale(2)          # the reference's -s table semantics (doubled, CINT-wrapped counts)
     score_scale = 2 if wname == "cfg5" else 1
@@ -390,8 +402,10 @@ def main():
         return ms, out, kernel_ms, (t0, t1)
 
     add_trees()
+    ctx.rebalance_shards()       # shard ranges for the class mix of these trees (same trees on every rank -> same ranges, no exchange)
     for _ in range(args.warmup):
         step_resident()
+    table_free = not ctx.table_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -429,6 +443,7 @@ def main():
         "kernel": "qs_count_rows_kernel", "kernel_ms": count_ms,
         "dist_kernel_ms": statistics.mean(t["dist_ms"] for t in kt), "score_kernel_ms": statistics.mean(t["score_ms"] for t in kt),
         "peak_source": "measured live on this GPU: HSET2 (fp16x2 compare -> mask) lane-op rate in the kernel's own 2xHSET2+IADD3 mix (qs_measure_alu_peak)",
+        "enumeration_efficiency": None,
         "mix_ceiling": {"frac_of_peak": 0.855, "frac": achieved / (0.855 * hset2_peak),
                         "note": "the kernel pairs every HSET2 (ALU pipe) with an IMAD.IADD (FMA pipe); that pair issues at 3.42 of 4 warp-instr/clk/SM in isolation "
                                 "(tools/ubench_mix2.cu, profiles/r01_w_ubench_mix2.txt), i.e. 0.855 of the HSET2 peak is the most this instruction mix can reach"},
@@ -438,6 +453,11 @@ def main():
         "int32_equiv": {"achieved": INT32_LANEOPS_PER_EVAL * my_evals / (count_ms * 1e-3) / 1e12, "peak": int32_peak / 1e12, "unit": "Tlaneop/s",
                         "frac": INT32_LANEOPS_PER_EVAL * my_evals / (count_ms * 1e-3) / int32_peak,
                         "note": "SURVEY §8d accounting: 9 scalar int32 lane-ops per evaluation vs the measured INT32 (LOP3/IADD3) lane rate"},
+        "scan": None if table_free else {
+            "kernel": "qs_scan_kernel", "bound": "hbm", "kernel_ms": statistics.mean(t["score_ms"] for t in kt),
+            "algorithmic_bytes": (r1 - r0) * 3 * cint_bytes_for(m), "achieved_gbs": (r1 - r0) * 3 * cint_bytes_for(m) / (statistics.mean(t["score_ms"] for t in kt) * 1e-3) / 1e9,
+            "peak_gbs": hbm_peak_gbs(), "frac": (r1 - r0) * 3 * cint_bytes_for(m) / (statistics.mean(t["score_ms"] for t in kt) * 1e-3) / 1e9 / hbm_peak_gbs(),
+            "note": "the table scan reads every entry of this rank's table once (3 x CINT bytes per quartet); score_kernel_ms also holds the clearing of the per-pair arrays"},
         "hbm": {"algorithmic_bytes": (r1 - r0) * 6 + 2 * n * n * m, "achieved_gbs": ((r1 - r0) * 6 + 2 * n * n * m) / (count_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak_gbs(),
                 "note": "table written once + distance matrices read once; the path is ALU-bound by three orders of magnitude (traffic = ncu DRAM bytes of one launch)"},
     }

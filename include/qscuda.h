@@ -159,9 +159,19 @@ int qs_get_counts(qs_ctx* ctx, uint64_t rank_begin, uint64_t rank_end, void* out
 /* Rank range [begin,end) owned by this shard. */
 int qs_shard_range(const qs_ctx* ctx, uint64_t* rank_begin, uint64_t* rank_end);
 /* The sharding rule itself (pure function, no context): shard g of G owns the quartets whose largest id s3
- * lies in [s3_begin, s3_end), boundaries ~ n*(g/G)^(1/4) rounded to 8, i.e. the rank range
- * [C(s3_begin,4), C(s3_end,4)).  Output pointers may be NULL. */
+ * lies in [s3_begin, s3_end), i.e. the rank range [C(s3_begin,4), C(s3_end,4)); the boundaries equalise the counting
+ * kernel's cost (work items including their padding), not the number of quartets.  Output pointers may be NULL. */
 int qs_shard_bounds(int n_taxa, int shard_index, int shard_count, int* s3_begin, int* s3_end, uint64_t* rank_begin, uint64_t* rank_end);
+
+/* The default ranges assume that every gene tree needs all three topology compares (class B).  Gene trees that contain all
+ * taxa and are fully resolved (class A) skip one role, which moves the cost balance between low and high s3; once the trees
+ * are added, qs_rebalance_shards classifies them (distance kernels only) and re-cuts the ranges for the observed class mix.
+ * Every shard must call it with the same trees (they then agree without talking to each other); *changed = 1 if this
+ * shard's range moved — counts and scores of earlier calls are invalid then, call qs_count again.  Optional: results do not
+ * depend on it, only the balance.  qs_table_resident: 1 if the last qs_count left this shard's table in device memory
+ * (QS_MODE_TABLE, or QS_MODE_AUTO when it fits), 0 if it ran table-free. */
+int qs_rebalance_shards(qs_ctx* ctx, int* changed);
+int qs_table_resident(const qs_ctx* ctx, int* resident);
 
 /* Diagnostics of the counting kernel's host-built task table for the quartets with s3 in [s3_begin, s3_end)
  * (pure host function, no context, no GPU).  stats[15] = {X tasks, Y tasks, XO items, XD items, Y items,

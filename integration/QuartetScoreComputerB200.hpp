@@ -185,6 +185,7 @@ QuartetScoreComputer<CINT>::QuartetScoreComputer(Tree const& refTree, const std:
         }
         qs_flat_trees_free(flat);
     }
+    for (auto c : ctxs) qs_check(c, qs_rebalance_shards(c, nullptr), "qs_rebalance_shards");      // shard ranges for the class mix of these trees
     std::cout << "Finished parsing evaluation trees.\n";
 
     // count + partial scores per shard (one host thread per GPU), reduce on the host

@@ -49,6 +49,8 @@ SIGNATURES = {
     "qs_get_counts": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.c_void_p]),
     "qs_shard_range": (C.c_int, [C.c_void_p, _u64p, _u64p]),
     "qs_shard_bounds": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _u64p, _u64p]),
+    "qs_rebalance_shards": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    "qs_table_resident": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     "qs_plan_stats": (C.c_int, [C.c_int, C.c_int, C.c_int, _i64p]),
     "qs_get_distances": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_uint16)]),
     "qs_write_raw_qic": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.c_char_p]),

@@ -183,6 +183,18 @@ class Context:
         self._check(self._lib.qs_score_finish(self._h, int(exact_qp), _ptr(lq, C.c_double), _ptr(qp, C.c_double), _ptr(eqp, C.c_double)), "qs_score_finish")
         return lq, qp, eqp
 
+    def rebalance_shards(self) -> bool:
+        """Re-cut the shard ranges for the class mix of the trees added so far (every shard must call it); True if this
+        shard's range moved (count again)."""
+        ch = C.c_int()
+        self._check(self._lib.qs_rebalance_shards(self._h, C.byref(ch)), "qs_rebalance_shards")
+        return bool(ch.value)
+
+    def table_resident(self) -> bool:
+        v = C.c_int()
+        self._check(self._lib.qs_table_resident(self._h, C.byref(v)), "qs_table_resident")
+        return bool(v.value)
+
     def shard_range(self):
         a, b = C.c_uint64(), C.c_uint64()
         self._check(self._lib.qs_shard_range(self._h, C.byref(a), C.byref(b)), "qs_shard_range")

@@ -157,41 +157,51 @@ int dev_alloc(qs_ctx* c, T** p, size_t count) {
 
 // Split of the rank space by the outer index d into G contiguous ranges of (nearly) equal COUNTING COST — not equal
 // quartet counts: what a shard pays is the work items of the counting kernel (kernels/count_rows.cuh), i.e. 8 x 8 blocks
-// including their padding.  Per d: the role-X items of all c < d; per block of 8 consecutive d: the role-Y items of all
+// including their padding.  Per d: the role-X items of all c < d (full blocks at 1, ragged-block items by the share of the
+// block they run over, diagonal blocks at 1 or 1/2; a (c,d) never costs less than the share of a task it blocks when the
+// task's row budget, not its item count, ends the task — small c); per block of 8 consecutive d: the role-Y items of all
 // (b,c) below it, paid in full by every shard that touches the block (a shard boundary inside a d-block makes both
-// neighbours run it).  Measured item costs (round 1, class-B trees, profiles/r01_zj_*): 2.78e-5 ms per X item,
-// 2.12e-5 ms per Y item, hence the 0.76.  The boundaries minimise the largest shard cost (greedy fill under a
-// bisected threshold, exact for contiguous partitions of a monotone cost); pure function of (n, G): every rank computes
-// the same ranges.  (use_xo_diag is declared further down; its threshold is repeated here.)
-void shard_bounds(int n, int g, int G, int* d_begin, int* d_end) {
+// neighbours run it) and only by the class-B trees: weight 0.76 x class_b_fraction (measured item costs, round 1, class-B
+// trees, profiles/r01_zj_*: 2.78e-5 ms per X item, 2.12e-5 ms per Y item).  The boundaries minimise the largest shard cost
+// (greedy fill under a bisected threshold, exact for contiguous partitions of a monotone cost); a pure function of its
+// arguments: every rank computes the same ranges.  (use_xo_diag / cr_threads_for are declared further down; their rules
+// are repeated here.)
+void shard_bounds(int n, int g, int G, double class_b_fraction, int* d_begin, int* d_end) {
     if (G <= 1) { *d_begin = 3; *d_end = n; return; }
     const int xo_diag = n > 160 ? 1 : 0;
+    const double T = n <= 112 ? 512 : 256;                                              // thread-items per task
+    const double R = (double)std::max<size_t>(4, std::min<size_t>((size_t)n, (24 * 1024) / ((size_t)((n + 7) / 8 * 8) * 2))) - 1;   // d rows a task can stage
+    const double wy = 0.76 * std::min(1.0, std::max(0.0, class_b_fraction));
     std::vector<double> PX(n + 1, 0.0), PYb((n >> 3) + 2, 0.0);
     {
-        std::vector<double> A(n + 1, 0.0), B(n + 1, 0.0);       // prefix over c of the X items of one (c,d) / of the Y a-blocks of one (b,c)
+        std::vector<double> A(n + 1, 0.0), B(n + 1, 0.0);       // prefix over c of the X cost of one (c,d) / of the Y a-blocks of one (b,c)
         for (int c = 2; c < n; ++c) {
-            const int nb = (c + 7) >> 3, nd = ((c - 2) >> 3) + 1;
-            const double items = nb * (nb - 1) / 2 + (xo_diag ? nd : 0.5 * nd);      // XO blocks (+ diagonal blocks: XO items or half-cost XD items)
-            A[c + 1] = A[c] + items;
+            const int nf = c >> 3, rg = c & 7, nd = ((c - 2) >> 3) + 1;
+            double xo = nf * (nf - 1) / 2 + (xo_diag ? nf : 0), xr = 0, xd = xo_diag ? 0 : 0.5 * nd;
+            if (rg) xr = (nf + ((xo_diag && rg >= 2) ? 1 : 0)) * (0.14 + 0.86 * rg / 8.0);
+            if (xo > 0) xo = std::max(xo, T / R);
+            if (xr > 0) xr = std::max(xr, (0.14 + 0.86 * rg / 8.0) * T / R);
+            if (xd > 0) xd = std::max(xd, T / R);
+            A[c + 1] = A[c] + xo + xr + xd;
             double bc = 0;
             for (int bb = 1; bb < c; ++bb) bc += (bb + 7) >> 3;
             B[c + 1] = B[c] + bc;
         }
-        for (int d = 3; d < n; ++d) PX[d + 1] = PX[d] + A[d];                          // X items with this d: all c < d
+        for (int d = 3; d < n; ++d) PX[d + 1] = PX[d] + A[d];                          // X cost with this d: all c < d
         for (int k = 0; k <= (n - 1) >> 3; ++k) {                                       // Y items of d-block k: all (b,c) with c + 1 <= 8k + 7
             const int cmax = std::min(8 * k + 6, n - 2);
-            PYb[k + 1] = PYb[k] + (cmax >= 2 ? 0.76 * B[cmax + 1] : 0.0);
+            PYb[k + 1] = PYb[k] + (cmax >= 2 ? wy * B[cmax + 1] : 0.0);
         }
     }
     auto cost = [&](int b, int e) -> double {                                           // shard [b, e), b < e
         return PX[e] - PX[b] + (PYb[((e - 1) >> 3) + 1] - PYb[b >> 3]);
     };
-    // smallest threshold T for which greedy filling needs <= G shards
-    auto fill = [&](double T, std::vector<int>* out) -> int {
+    // smallest threshold for which greedy filling needs <= G shards
+    auto fill = [&](double thr, std::vector<int>* out) -> int {
         int cnt = 0, b = 3;
         while (b < n) {
             int e = b + 1;
-            while (e < n && cost(b, e + 1) <= T) ++e;
+            while (e < n && cost(b, e + 1) <= thr) ++e;
             ++cnt; b = e;
             if (out) out->push_back(e);
             if (cnt > G) return cnt;
@@ -1171,7 +1181,7 @@ int qs_create(qs_ctx** out, int n_taxa, int cint_bytes, int mode, int device, in
         c->host_only = true; c->device = device; c->n = n_taxa; c->n_pad = (n_taxa + 7) / 8 * 8; c->cint_bytes = cint_bytes;
         c->auto_mode = mode == QS_MODE_AUTO; c->mode = c->auto_mode ? QS_MODE_TABLE : mode;
         c->shard_index = shard_index; c->shard_count = shard_count;
-        shard_bounds(n_taxa, shard_index, shard_count, &c->d_begin, &c->d_end);
+        shard_bounds(n_taxa, shard_index, shard_count, 1.0, &c->d_begin, &c->d_end);
         c->rank_begin = binom4((uint64_t)c->d_begin); c->rank_end = binom4((uint64_t)c->d_end);
         *out = c;
         return QS_OK;
@@ -1187,7 +1197,7 @@ int qs_create(qs_ctx** out, int n_taxa, int cint_bytes, int mode, int device, in
     c->auto_mode = mode == QS_MODE_AUTO; c->mode = c->auto_mode ? QS_MODE_TABLE : mode;
     c->shard_index = shard_index; c->shard_count = shard_count;
     c->num_sms = prop.multiProcessorCount; c->smem_optin = (int)prop.sharedMemPerBlockOptin;
-    shard_bounds(n_taxa, shard_index, shard_count, &c->d_begin, &c->d_end);
+    shard_bounds(n_taxa, shard_index, shard_count, 1.0, &c->d_begin, &c->d_end);
     c->rank_begin = binom4((uint64_t)c->d_begin); c->rank_end = binom4((uint64_t)c->d_end);
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return QS_E_CUDA; }
     c->stream = c->own_stream;
@@ -1385,6 +1395,39 @@ int qs_count(qs_ctx* ctx) {
     return QS_OK;
 }
 
+int qs_rebalance_shards(qs_ctx* ctx, int* changed) {
+    if (!ctx) return QS_E_ARG;
+    if (changed) *changed = 0;
+    if (ctx->host_only) QS_FAIL(ctx, QS_E_STATE, "host-only context (QS_DEVICE_NONE): no device work; there is no CPU fallback");
+    if (ctx->m == 0) QS_FAIL(ctx, QS_E_STATE, "no evaluation trees were added");
+    if (ctx->shard_count == 1) return QS_OK;
+    QS_CUDA(ctx, cudaSetDevice(ctx->device));
+    int r;
+    if (!ctx->dist_valid) {                                    // classify the trees (the distance kernels do that; they are < 1 % of a step)
+        if ((r = run_distances(ctx))) return r;
+        QS_CUDA(ctx, cudaMemcpyAsync(ctx->h_flags + 2, ctx->d_nA, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->n_class_a = ctx->h_flags[2]; ctx->counted_once = true;
+    }
+    int b = 0, e = 0;
+    shard_bounds(ctx->n, ctx->shard_index, ctx->shard_count, (double)(ctx->m - ctx->n_class_a) / (double)ctx->m, &b, &e);
+    if (b == ctx->d_begin && e == ctx->d_end) return QS_OK;
+    QS_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_table) { cudaFree(ctx->d_table); ctx->d_table = nullptr; ctx->table_bytes = 0; }
+    ctx->d_begin = b; ctx->d_end = e;
+    ctx->rank_begin = binom4((uint64_t)b); ctx->rank_end = binom4((uint64_t)e);
+    ctx->plan_dB = ctx->plan_dE = -1; ctx->scan_dB = ctx->scan_dE = -1;
+    ctx->counted = false; ctx->fused_partials_valid = false; ctx->partials_ready = false;
+    if (changed) *changed = 1;
+    return QS_OK;
+}
+
+int qs_table_resident(const qs_ctx* ctx, int* resident) {
+    if (!ctx || !resident) return QS_E_ARG;
+    *resident = (ctx->mode == QS_MODE_TABLE) ? 1 : 0;
+    return QS_OK;
+}
+
 int qs_score_num_pairs(const qs_ctx* ctx, int64_t* n_pairs) {
     if (!ctx || !n_pairs) return QS_E_ARG;
     *n_pairs = (int64_t)ctx->ref.n_inner * ctx->ref.n_inner;
@@ -1477,7 +1520,7 @@ int qs_score(qs_ctx* ctx, int count_scale, int exact_qp, double* lqic, double* q
 int qs_shard_bounds(int n_taxa, int shard_index, int shard_count, int* s3_begin, int* s3_end, uint64_t* rank_begin, uint64_t* rank_end) {
     if (n_taxa < 4 || shard_count < 1 || shard_index < 0 || shard_index >= shard_count) return QS_E_ARG;
     int b = 0, e = 0;
-    shard_bounds(n_taxa, shard_index, shard_count, &b, &e);
+    shard_bounds(n_taxa, shard_index, shard_count, 1.0, &b, &e);
     if (s3_begin) *s3_begin = b;
     if (s3_end) *s3_end = e;
     if (rank_begin) *rank_begin = binom4((uint64_t)b);

@@ -493,3 +493,34 @@ def test_raw_qic_from_several_shards(golden, tmp_path):
         ctxs[1].write_raw_qic(ref.taxa, p)                 # one shard alone cannot write the file
     for c in ctxs:
         c.close()
+
+
+@pytest.mark.parametrize("kw", [dict(k_max=10), dict(k_max=10, p_missing=0.1, p_contract=0.1)])
+def test_rebalanced_shards_tile_the_rank_space_and_reproduce_single_shard(kw):
+    """qs_rebalance_shards re-cuts the ranges for the observed class mix (class A trees skip role Y): the ranges must still tile
+    the rank space, every shard must arrive at the same cut without talking to the others, and tables / scores must not change"""
+    s = SyntheticInput(60, 300, 44, want_newick=False, **kw)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    with run_ctx(ref, s.flat) as ctx:
+        full, want = ctx.get_counts(), ctx.score(1)
+    G, tables, lqs, sums, ranges, fin = 5, [], [], [], [], None
+    for g in range(G):
+        ctx = Context(ref.n_taxa, 2, shard_index=g, shard_count=G)
+        ctx.set_reference(ref)
+        ctx.add_trees(s.flat)
+        before = ctx.shard_range()
+        moved = ctx.rebalance_shards()
+        assert moved == (ctx.shard_range() != before)
+        ctx.count()
+        r0, r1 = ctx.shard_range()
+        ranges.append((r0, r1))
+        tables.append(ctx.get_counts(r0, r1))
+        lq, sm = ctx.score_partials(1)
+        lqs.append(lq); sums.append(sm)
+        if g == G - 1:
+            fin = ctx.score_finalize(np.minimum.reduce(lqs), np.add.reduce(sums))
+        ctx.close()
+    assert ranges[0][0] == 0 and ranges[-1][1] == len(full) and all(ranges[i][1] == ranges[i + 1][0] for i in range(G - 1))
+    assert np.array_equal(np.concatenate(tables), full)
+    for a, b in zip(fin, want):
+        assert np.array_equal(a, b)
