@@ -80,12 +80,14 @@ class ClockSampler:
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, gpu_index: int):
-        self.idx, self.rows, self.proc = gpu_index, [], None
+    def __init__(self, gpu_index: int, interval_ms: int = 20):
+        # the poll itself costs the sampled GPU a few per cent while it runs (rank 0's counting kernel was 4-7 % slower than the other
+        # ranks' with 50 polls per second): long timed regions are polled less often
+        self.idx, self.rows, self.proc, self.interval_ms = gpu_index, [], None, int(max(20, min(500, interval_ms)))
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20", "-i", str(self.idx)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(self.interval_ms), "-i", str(self.idx)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -403,10 +405,13 @@ def main():
 
     add_trees()
     ctx.rebalance_shards()       # shard ranges for the class mix of these trees (same trees on every rank -> same ranges, no exchange)
+    t_w = time.time()
     for _ in range(args.warmup):
         step_resident()
+    torch.cuda.synchronize()
+    step_s = (time.time() - t_w) / max(1, args.warmup)
     table_free = not ctx.table_resident()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, interval_ms=int(1e3 * step_s * args.steps / 25))      # ~25 samples over the timed region, at least every 500 ms
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
