@@ -20,6 +20,7 @@ per-node-pair topology sums (NCCL).  The job is fixed as N grows: "scaling": "st
 from __future__ import annotations
 
 import argparse
+import gc
 import hashlib
 import json
 import os
@@ -288,6 +289,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer leg (long workloads: cfg4/cfg5 exploration runs)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-clocks", action="store_true", help="diagnostic: do not poll nvidia-smi during the timed region (the line then has no clocks evidence)")
     args = ap.parse_args()
     if args.impl == "ours" and not args.no_e2e:
         args.warmup = max(args.warmup, 3)       # timing rule: W >= 3 (exploration runs with --no-e2e may use fewer)
@@ -385,18 +387,40 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    def host_state():
+        # who else used the host during the timed region: context switches of this process and the box's CPU time (jiffies) by kind
+        st = {}
+        try:
+            for line in open("/proc/self/status"):
+                if line.startswith(("voluntary_ctxt_switches", "nonvoluntary_ctxt_switches")):
+                    st[line.split(":")[0]] = int(line.split()[1])
+            f = open("/proc/stat").readline().split()
+            st.update(dict(zip(("user", "nice", "system", "idle", "iowait", "irq", "softirq", "steal"), (int(x) for x in f[1:9]))))
+        except Exception:
+            pass
+        return st
+
     def timed(fn, k):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gc.collect()
+        gc.disable()
+        hs0 = host_state()
         t0 = time.time()
         e0.record(stream)
         kernel_ms = []
         for _ in range(k):
+            ts = time.perf_counter()
             out = fn()
             kernel_ms.append(ctx.last_timing())
+            kernel_ms[-1]["host_wall_ms"] = 1e3 * (time.perf_counter() - ts)      # diagnostic: this step on the host clock (last_timing waits for the step's events)
         e1.record(stream)
         barrier()
         t1 = time.time()
+        hs1 = host_state()
+        gc.enable()
+        host_delta.clear()
+        host_delta.update({k_: hs1[k_] - hs0[k_] for k_ in hs0 if k_ in hs1})
         ms = e0.elapsed_time(e1)
         if dist is not None:
             t = torch.tensor([ms], device="cuda", dtype=torch.float64)
@@ -404,6 +428,7 @@ def main():
             ms = float(t.item())
         return ms, out, kernel_ms, (t0, t1)
 
+    host_delta = {}
     add_trees()
     ctx.rebalance_shards()       # shard ranges for the class mix of these trees (same trees on every rank -> same ranges, no exchange)
     t_w = time.time()
@@ -413,11 +438,20 @@ def main():
     step_s = (time.time() - t_w) / max(1, args.warmup)
     table_free = not ctx.table_resident()
     sampler = ClockSampler(local_rank, interval_ms=int(1e3 * step_s * args.steps / 25))      # ~25 samples over the timed region, at least every 500 ms
-    if rank == 0:
+    if rank == 0 and not args.no_clocks:
+        # nvidia-smi takes a few hundred ms to come up and holds driver locks while it does: the timed region starts only after its
+        # first sample has arrived; untimed steps keep the GPU busy meanwhile
         sampler.start()
-        time.sleep(0.25)
+        t_s = time.time()
+        while not sampler.rows and time.time() - t_s < 5.0:
+            if dist is None:
+                step_resident()
+            else:
+                time.sleep(0.01)           # (steps hold collectives: the other ranks wait at the timed region's first barrier instead)
+        torch.cuda.synchronize()
     l0 = ctx.launch_count()
     ms_res, scores, kt, span = timed(step_resident, args.steps)
+    host_res = dict(host_delta)
     launches = ctx.launch_count() - l0
     clocks = sampler.stop(*span) if rank == 0 else None
     if args.no_e2e:
@@ -492,6 +526,9 @@ def main():
         "golden": golden,
         "e2e_cli": cli,
         "clocks": clocks,
+        "host": host_res,          # context switches of this process and CPU jiffies of the box over the timed (resident) region
+        "step_wall_ms": [round(t["host_wall_ms"], 3) for t in kt],          # each timed step on the host clock and the sum of its three kernel groups:
+        "step_kernel_ms": [round(t["dist_ms"] + t["count_ms"] + t["score_ms"], 3) for t in kt],      # a gap between the two is host time (launches, jitter), not GPU work
         "roofline": roofline,
     }
 

@@ -43,7 +43,7 @@
 
 namespace qs {
 
-enum { ITEM_XO = 0, ITEM_XD = 1, ITEM_Y = 2, ITEM_XR = 3 };
+enum { ITEM_XO = 0, ITEM_XD = 1, ITEM_Y = 2, ITEM_XR = 3, ITEM_Z = 4, ITEM_KINDS = 5 };
 
 struct RowTask {
     int32_t kind;           // ITEM_*
@@ -60,6 +60,8 @@ struct EnumTables {
     const int64_t* PY;      // [n+1] Y items with b' < b
     const int64_t* CD;      // [n+1] d-blocks of role Y over c' < c
     const int64_t* PXR;     // [n+1] XR items with c' < c
+    const int64_t* PZ;      // [nz * n + 1] Z items before (d, a), d = cr_zd(index / n), a = index % n
+    int z_first, z_last;    // role Y owns the d-blocks inside [z_first, z_last) (multiples of 8, or both = d_end), role Z the d of [d_begin, z_first) and [z_last, d_end)
     int xo_diag;            // 1: diagonal blocks are ordinary XO items (ia <= ib) and there are no XD items (large n, where
                             //    XD tasks would be starved of items by the row budget and diagonal blocks are a few % of the work)
 };
@@ -120,9 +122,20 @@ __host__ __device__ __forceinline__ int cr_nxr(int c, int xo_diag) {
     return cr_nfull(c) + ((xo_diag && (c & 7) >= 2) ? 1 : 0);          // ia = 0 .. nfull-1 (+ the ragged diagonal block, if it holds two taxa)
 }
 __host__ __device__ __forceinline__ int cr_dlo(int c, int d_begin) { return c + 1 > d_begin ? c + 1 : d_begin; }
-__host__ __device__ __forceinline__ int cr_ndb(int c, int d_begin, int d_end) {                                    // d-blocks (of 8) above c
-    const int dlo = cr_dlo(c, d_begin);
-    return dlo < d_end ? ((d_end - 1) >> 3) - (dlo >> 3) + 1 : 0;
+// Role Y works on whole d-blocks of 8; the d of a block that the shard's range [d_begin, d_end) cuts belong to role Z instead (one d
+// per item, 8 x 8 blocks of (b,c)): as Y blocks both neighbours of a shard boundary paid the whole block (13 % of the counting time of
+// 8 shards at n = 500, profiles/r02_v_shards_*.txt), and the last block of an n that is no multiple of 8 ran half empty.
+__host__ __device__ __forceinline__ int cr_ndb(int c, int z_first, int z_last) {                                   // d-blocks of role Y above c
+    const int k0 = max((c + 1) >> 3, z_first >> 3);
+    return (z_last >> 3) > k0 ? (z_last >> 3) - k0 : 0;
+}
+__host__ __device__ __forceinline__ int cr_nzd(int d_begin, int d_end, int z_first, int z_last) { return (z_first - d_begin) + (d_end - z_last); }
+__host__ __device__ __forceinline__ int cr_zd(int i, int d_begin, int z_first, int z_last) { return i < z_first - d_begin ? d_begin + i : z_last + (i - (z_first - d_begin)); }
+// Z items of the pair (a,d): the blocks (ib <= ic) of the taxa strictly between a and d, j = ic'(ic'+1)/2 + ib' counted from block (a+1) >> 3
+__host__ __device__ __forceinline__ int cr_nz(int a, int d) {
+    if (d - a < 3) return 0;
+    const int k = ((d - 1) >> 3) - ((a + 1) >> 3) + 1;
+    return k * (k + 1) / 2;
 }
 // largest x in [lo,hi) with P[x] <= key  (P non-decreasing, P[lo] <= key)
 __host__ __device__ __forceinline__ int cr_ub(const int64_t* P, int lo, int hi, int64_t key) {
@@ -141,14 +154,27 @@ __host__ __device__ __forceinline__ void cr_decode_x(const int64_t* P, int kind,
     j = (int)(r % cnt);
 }
 // item e of kind Y -> (b, c, a-block ia, d-block id)
-__host__ __device__ __forceinline__ void cr_decode_y(const EnumTables& E, int64_t e, int n, int d_begin, int& b, int& c, int& ia, int& id) {
+__host__ __device__ __forceinline__ void cr_decode_y(const EnumTables& E, int64_t e, int n, int& b, int& c, int& ia, int& id) {
     b = cr_ub(E.PY, 0, n, e);
     const int64_t r = e - E.PY[b];
     const int na = (b + 7) >> 3;
     ia = (int)(r % na);
     const int64_t target = E.CD[b + 1] + r / na;
     c = cr_ub(E.CD, b + 1, n, target);
-    id = (cr_dlo(c, d_begin) >> 3) + (int)(target - E.CD[c]);
+    id = max((c + 1) >> 3, E.z_first >> 3) + (int)(target - E.CD[c]);
+}
+// item e of kind Z -> (d, a, block pair ib <= ic)
+__host__ __device__ __forceinline__ void cr_decode_z(const EnumTables& E, int64_t e, int n, int d_begin, int d_end, int& d, int& a, int& ib, int& ic) {
+    const int z = cr_ub(E.PZ, 0, cr_nzd(d_begin, d_end, E.z_first, E.z_last) * n, e);
+    d = cr_zd(z / n, d_begin, E.z_first, E.z_last);
+    a = z % n;
+    const int j = (int)(e - E.PZ[z]);
+    int t = (int)((sqrtf(8.f * (float)j + 1.f) - 1.f) * 0.5f);
+    while (t * (t + 1) / 2 > j) --t;
+    while ((t + 1) * (t + 2) / 2 <= j) ++t;
+    const int k0 = (a + 1) >> 3;
+    ic = k0 + t;
+    ib = k0 + (j - t * (t + 1) / 2);
 }
 
 // add v (mod 2^32, may stand for a negative number) to element `elem` of the CINT table
@@ -413,11 +439,48 @@ __global__ void __launch_bounds__(THREADS, cr_ctas_per_sm(THREADS)) qs_count_row
             };
             if (vA) flush(cA, dA, jA, ga);
             if (vB) flush(cB, dB, jB, gb);
+        } else if (T.kind == ITEM_Z) {   // pair (p,q) = (a,d), u = b-block, v = c-block: G(b) > G(c) -> ab|cd (slot 0)
+            const bool vA = 2 * tid < T.ne, vB = 2 * tid + 1 < T.ne;
+            int dA = 3, aA = 0, ibA = 0, icA = 0, dB = 3, aB = 0, ibB = 0, icB = 0;
+            if (vA) cr_decode_z(a.E, T.e0 + 2 * tid, a.n, a.d_begin, a.d_end, dA, aA, ibA, icA);
+            if (vB) cr_decode_z(a.E, T.e0 + 2 * tid + 1, a.n, a.d_begin, a.d_end, dB, aB, ibB, icB);
+            const uint32_t pA = vA ? cr_row_off(T, aA, rb) : 0u, qA = vA ? cr_row_off(T, dA, rb) : 0u;
+            const uint32_t pB = vB ? cr_row_off(T, aB, rb) : 0u, qB = vB ? cr_row_off(T, dB, rb) : 0u;
+            const uint32_t oApu = pA + ibA * 16u, oAqu = qA + ibA * 16u, oApv = pA + icA * 16u, oAqv = qA + icA * 16u;
+            const uint32_t oBpu = pB + ibB * 16u, oBqu = qB + ibB * 16u, oBpv = pB + icB * 16u, oBqv = qB + icB * 16u;
+            GCounters ga, gb; zero(ga); zero(gb);
+            stream_rows<THREADS>(a, P, T, t0, t1, [&](const unsigned char* base, int nt, uint32_t slot) {
+                stage_halves(base, nt, slot,
+                             [&](const unsigned char* s) { return BlockRows{lds128(s, oApu), lds128(s, oAqu), lds128(s, oApv), lds128(s, oAqv)}; },
+                             [&](const unsigned char* s) { return BlockRows{lds128(s, oBpu), lds128(s, oBqu), lds128(s, oBpv), lds128(s, oBqv)}; },
+                             [&](const BlockRows& r) { step_gt(ga, r); }, [&](const BlockRows& r) { step_gt(gb, r); });
+            });
+            auto flush = [&](int d, int a0, int ib, int ic, const GCounters& g) {
+                const uint64_t rd = binom4((uint64_t)d) - a.rank_base + (uint64_t)a0;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    const int c = ic * 8 + jj;
+                    if (c >= d) continue;
+                    const uint64_t rc = rd + binom3((uint64_t)c);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        uint32_t h[2];
+                        decode(g.gt[jj][p], h[0], h[1]);
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int b = ib * 8 + 2 * p + e;
+                            if (b > a0 && b < c) table_red(a.table, a.cint_bytes, (rc + (uint64_t)b * (b - 1) / 2) * 3, h[e]);
+                        }
+                    }
+                }
+            };
+            if (vA) flush(dA, aA, ibA, icA, ga);
+            if (vB) flush(dB, aB, ibB, icB, gb);
         } else {   // ITEM_Y: pair (p,q) = (b,c), u = a-block, v = d-block
             const bool vA = 2 * tid < T.ne, vB = 2 * tid + 1 < T.ne;
             int bA = 1, cA = 2, iaA = 0, idA = 0, bB = 1, cB = 2, iaB = 0, idB = 0;
-            if (vA) cr_decode_y(a.E, T.e0 + 2 * tid, a.n, a.d_begin, bA, cA, iaA, idA);
-            if (vB) cr_decode_y(a.E, T.e0 + 2 * tid + 1, a.n, a.d_begin, bB, cB, iaB, idB);
+            if (vA) cr_decode_y(a.E, T.e0 + 2 * tid, a.n, bA, cA, iaA, idA);
+            if (vB) cr_decode_y(a.E, T.e0 + 2 * tid + 1, a.n, bB, cB, iaB, idB);
             const uint32_t pA = vA ? cr_row_off(T, bA, rb) : 0u, qA = vA ? cr_row_off(T, cA, rb) : 0u;
             const uint32_t pB = vB ? cr_row_off(T, bB, rb) : 0u, qB = vB ? cr_row_off(T, cB, rb) : 0u;
             const uint32_t oApu = pA + iaA * 16u, oAqu = qA + iaA * 16u, oApv = pA + idA * 16u, oAqv = qA + idA * 16u;

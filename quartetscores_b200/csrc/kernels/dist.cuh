@@ -132,15 +132,48 @@ __global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
 // ---- warp-per-tree variant for small gene trees ------------------------------------------------------------
 // The CTA-per-tree kernel above leaves 255 threads idle while one thread walks the tree, and at 100 taxa that
 // serial walk is most of its time (0.78 ms for 10,000 trees, profiles/r01_e_launches.csv).  Here every WARP owns a
-// tree: up to 64 trees per SM are in flight, lane 0 runs three short index-order passes instead of a stack DFS
-// (valid because parent[i] < i): depths + child counts (forward), leaves per subtree (backward), first leaf
-// position of every subtree (forward).  Everything else — validation, the leaf arrays, the turning depths
-// lh[q] = depth of lca(leaf q, leaf q+1), written by the unique non-first child whose subtree starts at q+1 — and
-// the pair sweep run on all 32 lanes.  Any planar order gives the same matrix; this one lists children by index.
+// tree, up to 64 trees per SM are in flight, and nothing is walked by one thread: with parent[i] < i as the only
+// assumption about the node order,
+//   * depth[i] and, later, the tour position of the first leaf of subtree i are sums along the root path: pointer
+//     jumping on packed (ancestor, partial sum) words, in place — a node reads its ancestor's word in one 32-bit load, so
+//     any interleaving of the lanes keeps "sum over the path up to, not including, the ancestor" true; ~log2(depth) rounds;
+//   * child counts, leaves per subtree (every leaf adds one to each of its ancestors) and a child's offset inside its
+//     parent's leaf interval (fetch-and-add of its leaf count on the parent: children are placed in arrival order, any
+//     planar order gives the same matrix) are shared-memory atomics on 16-bit fields;
+//   * a tree whose leaves lie deeper than 16 edges on average (caterpillars) counts its subtree leaves in one serial
+//     backward pass instead, as round 1 did for every tree.
+// Validation, the leaf arrays, the turning depths lh[q] = depth of lca(leaf q, leaf q+1), written by the unique non-first
+// child whose subtree starts at q+1, and the pair sweep run on all 32 lanes as before.
 constexpr int DW_WARPS = 8;
 constexpr int DW_ARRAYS = 10;    // int16 arrays of max_nodes entries per warp
 __host__ __device__ __forceinline__ size_t dist_warp_smem_per_warp(int max_nodes, int n) {
     return (size_t)DW_ARRAYS * 2 * ((max_nodes + 7) / 8 * 8) + (size_t)((n + 31) / 32) * 4;
+}
+
+// 16-bit field of a shared int16 array, += v through the 32-bit word that holds it (fields stay < 32768: no carry); returns the old field
+__device__ __forceinline__ int dw_add16(int16_t* arr, int idx, int v) {
+    const uint32_t sh = (uint32_t)(idx & 1) * 16u;
+    const uint32_t old = atomicAdd(reinterpret_cast<uint32_t*>(arr) + (idx >> 1), (uint32_t)v << sh);
+    return (int)((old >> sh) & 0xffffu);
+}
+// words (ancestor << 16 | sum of the weights from the node up to, not including, that ancestor); the root is node 0 with
+// weight 0.  On return every ancestor is 0 and the low halves hold the sums over the whole root paths.
+__device__ __forceinline__ void dw_jump(volatile uint32_t* pj, int N, int lane) {
+    bool again;
+    do {
+        again = false;
+        for (int i = lane; i < N; i += 32) {
+            const uint32_t w = pj[i];
+            const uint32_t anc = w >> 16;
+            if (anc != 0u) {
+                const uint32_t wa = pj[anc];
+                pj[i] = (wa & 0xffff0000u) | ((w + wa) & 0xffffu);
+                again |= (wa >> 16) != 0u;
+            }
+        }
+        __syncwarp();
+        again = __any_sync(0xffffffffu, again);
+    } while (again);
 }
 
 __global__ void __launch_bounds__(32 * DW_WARPS) qs_dist_warp_kernel(DistArgs a) {
@@ -153,12 +186,13 @@ __global__ void __launch_bounds__(32 * DW_WARPS) qs_dist_warp_kernel(DistArgs a)
     int16_t* cnt = dep + NP;                           // number of children
     int16_t* lfc = cnt + NP;                           // leaves in the subtree
     int16_t* off = lfc + NP;                           // tour position of the subtree's first leaf
-    int16_t* nf = off + NP;                            // next free position while children are placed
+    int16_t* nf = off + NP;                            // leaves of the children placed so far
     int16_t* lid = nf + NP;                            // taxon id (-1: none)
     int16_t* ltid = lid + NP;                          // per tour position: taxon id,
     int16_t* ldep = ltid + NP;                         //   depth,
     int16_t* lh = ldep + NP;                           //   depth of lca(leaf q, leaf q+1)
     uint32_t* seen = reinterpret_cast<uint32_t*>(lh + NP);
+    volatile uint32_t* pj = reinterpret_cast<volatile uint32_t*>(ltid);   // pointer-jumping words, over ltid + ldep (filled after the jumps)
     const unsigned FULL = 0xffffffffu;
     int local_max = 0;
     const int gw = blockIdx.x * DW_WARPS + warp, stride = gridDim.x * DW_WARPS;
@@ -171,19 +205,45 @@ __global__ void __launch_bounds__(32 * DW_WARPS) qs_dist_warp_kernel(DistArgs a)
         for (int i = lane; i < N; i += 32) {
             int p = a.parent[o + i];
             if (i > 0 && (p < 0 || p >= i)) { bad = 1; p = 0; }
-            par[i] = (int16_t)p; cnt[i] = 0; lfc[i] = 0;
+            par[i] = (int16_t)p; cnt[i] = 0; lfc[i] = 0; nf[i] = 0;
             const int id = a.leaf_id[o + i];
             lid[i] = (int16_t)((id >= 0 && id < a.n) ? id : (id < 0 ? -1 : -2));
         }
         for (int i = lane; i < nw; i += 32) seen[i] = 0u;
         __syncwarp();
-        if (lane == 0) {
-            dep[0] = 0; off[0] = 0; nf[0] = 0;
-            for (int i = 1; i < N; ++i) { const int p = par[i]; dep[i] = dep[p] + 1; cnt[p] = cnt[p] + 1; }
+        // depths; child counts
+        for (int i = lane; i < N; i += 32) {
+            pj[i] = i > 0 ? (((uint32_t)par[i] << 16) | 1u) : 0u;
+            if (i > 0) dw_add16(cnt, par[i], 1);
+        }
+        __syncwarp();
+        dw_jump(pj, N, lane);
+        int sumdep = 0;
+        for (int i = lane; i < N; i += 32) {
+            const int d = (int)(pj[i] & 0xffffu);
+            dep[i] = (int16_t)d;
+            if (cnt[i] == 0) sumdep += d;
+        }
+        for (int s = 16; s > 0; s >>= 1) sumdep += __shfl_xor_sync(FULL, sumdep, s);
+        __syncwarp();
+        // leaves per subtree
+        if (sumdep <= 16 * N + 64) {
+            for (int i = lane; i < N; i += 32)
+                if (cnt[i] == 0) {
+                    int p = i;
+                    dw_add16(lfc, p, 1);
+                    while (p != 0) { p = par[p]; dw_add16(lfc, p, 1); }
+                }
+        } else if (lane == 0) {
             for (int i = N - 1; i >= 1; --i) { const int l = cnt[i] == 0 ? 1 : lfc[i]; lfc[i] = (int16_t)l; lfc[par[i]] = lfc[par[i]] + l; }
             if (cnt[0] == 0) lfc[0] = 1;
-            for (int i = 1; i < N; ++i) { const int p = par[i]; const int q = nf[p]; off[i] = (int16_t)q; nf[i] = (int16_t)q; nf[p] = (int16_t)(q + lfc[i]); }
         }
+        __syncwarp();
+        // tour position of the first leaf of every subtree: the leaves of the earlier siblings, summed along the root path
+        for (int i = lane; i < N; i += 32) pj[i] = i > 0 ? (((uint32_t)par[i] << 16) | (uint32_t)dw_add16(nf, par[i], lfc[i])) : 0u;
+        __syncwarp();
+        dw_jump(pj, N, lane);
+        for (int i = lane; i < N; i += 32) off[i] = (int16_t)(pj[i] & 0xffffu);
         __syncwarp();
         // validation, degrees, leaf arrays, turning depths: all lanes
         int maxdeg = 0;

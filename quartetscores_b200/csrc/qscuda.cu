@@ -34,6 +34,7 @@ using namespace qs;
 
 namespace {
 
+
 constexpr int kMaxHalfExact = 2048;     // integers up to 2048 are exact in fp16 (distances; the counters are integer)
 constexpr size_t kTableSlack = 64;      // the scan reads the table in 48-byte groups: the last one may reach past the last entry
 
@@ -53,7 +54,7 @@ struct HostRef {
 struct qs_ctx {
     int device = 0, n = 0, n_pad = 0, cint_bytes = 2, mode = 0, shard_index = 0, shard_count = 1;
     bool host_only = false;      // QS_DEVICE_NONE: reference bookkeeping + qs_score_finalize only
-    bool auto_mode = false;      // QS_MODE_AUTO: `mode` is re-decided by every qs_count (table if it fits this device, else table-free)
+    bool auto_mode = false;      // QS_MODE_AUTO: `mode` is decided by qs_count whenever the table size or the tree count changed (table if it fits this device, else table-free)
     int* h_flags = nullptr;      // pinned: {max distance, tree error, |A|} read back asynchronously by qs_count
     int d_begin = 0, d_end = 0, num_sms = 148, smem_optin = 0;
     uint64_t rank_begin = 0, rank_end = 0;
@@ -111,7 +112,9 @@ struct qs_ctx {
     std::vector<float> plan_xcost, plan_ycost;
     int64_t chunk_key[4] = {-1, -1, -1, -1}, chunk_choice = 1;      // cached chunk count for (plan generation, m, |A| hint, CTA slots)
     int64_t plan_generation = 0;
-    int64_t* d_enum = nullptr;   // PXO | PXD | PY | CD prefix tables of the plan
+    int64_t* d_enum = nullptr;   // PXO | PXD | PY | CD | PXR | PZ prefix tables of the plan
+    size_t enum_cap = 0;
+    int plan_zF = 0, plan_zL = 0;
     bool counted = false;
     bool counted_once = false;   // n_class_a holds the class split of an earlier qs_count on this context
 
@@ -124,6 +127,8 @@ struct qs_ctx {
     bool fused_partials_valid = false;   // table-free mode: partials accumulated by qs_count
     int fused_scale = 1;
     bool partials_ready = false;         // the device partials hold a finished scan (qs_score_scan / table-free qs_count)
+    size_t auto_need = ~(size_t)0;       // QS_MODE_AUTO: the table size and tree count the current mode was chosen for
+    int64_t auto_m = -1;
 
 };
 
@@ -159,20 +164,22 @@ int dev_alloc(qs_ctx* c, T** p, size_t count) {
 // quartet counts: what a shard pays is the work items of the counting kernel (kernels/count_rows.cuh), i.e. 8 x 8 blocks
 // including their padding.  Per d: the role-X items of all c < d (full blocks at 1, ragged-block items by the share of the
 // block they run over, diagonal blocks at 1 or 1/2; a (c,d) never costs less than the share of a task it blocks when the
-// task's row budget, not its item count, ends the task — small c); per block of 8 consecutive d: the role-Y items of all
-// (b,c) below it, paid in full by every shard that touches the block (a shard boundary inside a d-block makes both
-// neighbours run it) and only by the class-B trees: weight 0.76 x class_b_fraction (measured item costs, round 1, class-B
-// trees, profiles/r01_zj_*: 2.78e-5 ms per X item, 2.12e-5 ms per Y item).  The boundaries minimise the largest shard cost
+// task's row budget, not its item count, ends the task — small c); per whole block of 8 consecutive d inside the shard: the
+// role-Y items of all (b,c) below it; per d of a block the shard's range cuts: its role-Z items (z_split, declared below); both
+// only for the class-B trees: weight 0.76 x class_b_fraction (measured item costs, round 1, class-B trees,
+// profiles/r01_zj_*: 2.78e-5 ms per X item, 2.12e-5 ms per Y item).  The boundaries minimise the largest shard cost
 // (greedy fill under a bisected threshold, exact for contiguous partitions of a monotone cost); a pure function of its
 // arguments: every rank computes the same ranges.  (use_xo_diag / cr_threads_for are declared further down; their rules
 // are repeated here.)
+void z_split(int dB, int dE, int* z_first, int* z_last);
+
 void shard_bounds(int n, int g, int G, double class_b_fraction, int* d_begin, int* d_end) {
     if (G <= 1) { *d_begin = 3; *d_end = n; return; }
     const int xo_diag = n > 160 ? 1 : 0;
     const double T = n <= 112 ? 512 : 256;                                              // thread-items per task
     const double R = (double)std::max<size_t>(4, std::min<size_t>((size_t)n, (24 * 1024) / ((size_t)((n + 7) / 8 * 8) * 2))) - 1;   // d rows a task can stage
     const double wy = 0.76 * std::min(1.0, std::max(0.0, class_b_fraction));
-    std::vector<double> PX(n + 1, 0.0), PYb((n >> 3) + 2, 0.0);
+    std::vector<double> PX(n + 1, 0.0), PYb((n >> 3) + 2, 0.0), PZc(n + 2, 0.0);
     {
         std::vector<double> A(n + 1, 0.0), B(n + 1, 0.0);       // prefix over c of the X cost of one (c,d) / of the Y a-blocks of one (b,c)
         for (int c = 2; c < n; ++c) {
@@ -193,8 +200,15 @@ void shard_bounds(int n, int g, int G, double class_b_fraction, int* d_begin, in
             PYb[k + 1] = PYb[k] + (cmax >= 2 ? wy * B[cmax + 1] : 0.0);
         }
     }
+    for (int d = 0; d <= n; ++d) {                                                      // Z items of one d: all a <= d - 3
+        double z = 0;
+        if (d < n) for (int a = 0; a + 3 <= d; ++a) z += cr_nz(a, d);
+        PZc[d + 1] = PZc[d] + 0.82 * wy * z;          // a Z item against a Y item: fewer rows staged per task (8 shards of n = 500, profiles/r02_y_shards.txt)
+    }
     auto cost = [&](int b, int e) -> double {                                           // shard [b, e), b < e
-        return PX[e] - PX[b] + (PYb[((e - 1) >> 3) + 1] - PYb[b >> 3]);
+        int zf, zl;
+        z_split(b, e, &zf, &zl);
+        return PX[e] - PX[b] + (PYb[zl >> 3] - PYb[zf >> 3]) + (PZc[zf] - PZc[b]) + (PZc[e] - PZc[zl]);
     };
     // smallest threshold for which greedy filling needs <= G shards
     auto fill = [&](double thr, std::vector<int>* out) -> int {
@@ -298,28 +312,52 @@ int run_distances(qs_ctx* c) {
 
 // ---- task table of the counting kernel for the quartets with d in [dB, dE) (see kernels/count_rows.cuh) ----
 struct HostEnum {
-    std::vector<int64_t> PXO, PXD, PY, CD, PXR;
+    std::vector<int64_t> PXO, PXD, PY, CD, PXR, PZ;
+    int z_first = 0, z_last = 0;
     int xo_diag = 0;
-    EnumTables view() const { return EnumTables{PXO.data(), PXD.data(), PY.data(), CD.data(), PXR.data(), xo_diag}; }
+    EnumTables view() const { return EnumTables{PXO.data(), PXD.data(), PY.data(), CD.data(), PXR.data(), PZ.data(), z_first, z_last, xo_diag}; }
+    const int64_t* prefix(int kind) const { return kind == ITEM_XO ? PXO.data() : kind == ITEM_XD ? PXD.data() : kind == ITEM_XR ? PXR.data() : kind == ITEM_Y ? PY.data() : PZ.data(); }
+    int64_t total(int kind) const { return kind == ITEM_XO ? PXO.back() : kind == ITEM_XD ? PXD.back() : kind == ITEM_XR ? PXR.back() : kind == ITEM_Y ? PY.back() : PZ.back(); }
 };
 
 // separate half-cost tasks for the diagonal blocks pay off while a task's rows can cover most of the matrix
 int use_xo_diag(int n) { return n > 160 ? 1 : 0; }
 
+// which d of [dB, dE) role Y takes (whole d-blocks) and which role Z (kernels/count_rows.cuh): Z gets the d of the blocks the range
+// cuts; a range with fewer than 8 whole blocks goes to Z altogether — its role-Y tasks would hold a handful of items per matrix
+// row and be bound by staging the rows, not by comparing (the narrow shards of many GPUs: 8 shards of n = 500 count in 47-50 ms each
+// with Z against 52-56 ms with Y, profiles/r02_w2_shards_n500B.txt); over a wide range Y is the faster one (n = 500, one shard: 389 ms
+// against 396 ms with Z for every d, profiles/r02_x_z_everywhere.txt) — its 8 consecutive a are neighbours in the table, Z's flush scatters
+void z_split(int dB, int dE, int* z_first, int* z_last) {
+    int zf = std::min(dE, (dB + 7) & ~7), zl = std::max(zf, dE & ~7);
+    int min_blocks = 8, max_span = 80;
+    if (const char* env = getenv("QS_Z_MIN_BLOCKS")) min_blocks = atoi(env);         // tuning hooks
+    if (const char* env = getenv("QS_Z_MAX_SPAN")) max_span = atoi(env);
+    if (((zl - zf) >> 3) < min_blocks && dE - dB <= max_span) zf = zl = dE;
+    *z_first = zf; *z_last = zl;
+}
+
 void build_enum_tables(int n, int dB, int dE, HostEnum& H) {
     H.xo_diag = use_xo_diag(n);
+    z_split(dB, dE, &H.z_first, &H.z_last);
     H.PXO.assign(n + 1, 0); H.PXD.assign(n + 1, 0); H.PY.assign(n + 1, 0); H.CD.assign(n + 1, 0); H.PXR.assign(n + 1, 0);
     for (int c = 0; c < n; ++c) {
         const int64_t nd = (c >= 2) ? std::max(0, dE - cr_dlo(c, dB)) : 0;
         H.PXO[c + 1] = H.PXO[c] + nd * cr_nxo(c, H.xo_diag);
         H.PXD[c + 1] = H.PXD[c] + nd * cr_nxd(c, H.xo_diag);
         H.PXR[c + 1] = H.PXR[c] + nd * cr_nxr(c, H.xo_diag);
-        H.CD[c + 1] = H.CD[c] + ((c >= 2) ? cr_ndb(c, dB, dE) : 0);
+        H.CD[c + 1] = H.CD[c] + ((c >= 2) ? cr_ndb(c, H.z_first, H.z_last) : 0);
     }
     for (int b = 0; b < n; ++b) {
         int64_t items = 0;
         if (b >= 1 && b + 1 < n) items = (int64_t)((b + 7) / 8) * (H.CD[n] - H.CD[b + 1]);
         H.PY[b + 1] = H.PY[b] + items;
+    }
+    const int nz = dB < dE ? cr_nzd(dB, dE, H.z_first, H.z_last) : 0;
+    H.PZ.assign((size_t)nz * n + 1, 0);
+    for (int i = 0; i < nz; ++i) {
+        const int d = cr_zd(i, dB, H.z_first, H.z_last);
+        for (int a = 0; a < n; ++a) H.PZ[(size_t)i * n + a + 1] = H.PZ[(size_t)i * n + a] + cr_nz(a, d);
     }
 }
 
@@ -327,22 +365,25 @@ void build_enum_tables(int n, int dB, int dE, HostEnum& H) {
 void task_row_intervals(const HostEnum& H, int kind, int64_t e0, int ne, int n, int dB, int dE, std::vector<std::pair<int, int>>& iv) {
     iv.clear();
     int p0, q0, p1, q1, t0, t1;
-    if (kind == ITEM_Y) {
-        cr_decode_y(H.view(), e0, n, dB, p0, q0, t0, t1);
-        cr_decode_y(H.view(), e0 + ne - 1, n, dB, p1, q1, t0, t1);
+    if (kind == ITEM_Z) {
+        cr_decode_z(H.view(), e0, n, dB, dE, p0, q0, t0, t1);
+        cr_decode_z(H.view(), e0 + ne - 1, n, dB, dE, p1, q1, t0, t1);
+    } else if (kind == ITEM_Y) {
+        cr_decode_y(H.view(), e0, n, p0, q0, t0, t1);
+        cr_decode_y(H.view(), e0 + ne - 1, n, p1, q1, t0, t1);
     } else {
-        const int64_t* P = kind == ITEM_XO ? H.PXO.data() : kind == ITEM_XR ? H.PXR.data() : H.PXD.data();
-        cr_decode_x(P, kind, H.xo_diag, e0, n, dB, p0, q0, t0);
-        cr_decode_x(P, kind, H.xo_diag, e0 + ne - 1, n, dB, p1, q1, t0);
+        cr_decode_x(H.prefix(kind), kind, H.xo_diag, e0, n, dB, p0, q0, t0);
+        cr_decode_x(H.prefix(kind), kind, H.xo_diag, e0 + ne - 1, n, dB, p1, q1, t0);
     }
     // outer (fixed) rows p0..p1; inner (variable) rows: tail of p0, everything of the rows in between, head of p1
-    const int qmax = (kind == ITEM_Y) ? dE - 2 : dE - 1;                 // last inner row that has items
-    auto qlo = [&](int p) { return (kind == ITEM_Y) ? p + 1 : cr_dlo(p, dB); };
+    //   X kinds: outer c, inner d in [dlo(c), dE);   Y: outer b, inner c in (b, z_last - 2];   Z: outer d (one of Z's two runs of d), inner a in [0, d - 3]
+    auto qlo = [&](int p) { return kind == ITEM_Z ? 0 : kind == ITEM_Y ? p + 1 : cr_dlo(p, dB); };
+    auto qhi = [&](int p) { return kind == ITEM_Z ? p - 3 : kind == ITEM_Y ? H.z_last - 2 : dE - 1; };
     iv.emplace_back(p0, p1);
     if (p0 == p1) iv.emplace_back(q0, q1);
     else {
-        iv.emplace_back(q0, qmax);
-        if (p1 - p0 >= 2) iv.emplace_back(qlo(p0 + 1), qmax);
+        iv.emplace_back(q0, qhi(p0));
+        if (p1 - p0 >= 2) iv.emplace_back(qlo(p0 + 1), std::max(qhi(p0 + 1), qhi(p1 - 1)));
         iv.emplace_back(qlo(p1), q1);
     }
     std::sort(iv.begin(), iv.end());
@@ -365,8 +406,8 @@ void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, int
     xt.clear(); yt.clear();
     std::vector<std::pair<int, int>> iv;
     auto rows_of = [&](const std::vector<std::pair<int, int>>& v) { int r = 0; for (auto& x : v) r += x.second - x.first + 1; return r; };
-    auto emit = [&](std::vector<RowTask>& out, int kind, int64_t total, int cap) {
-        int64_t e = 0;
+    auto emit = [&](std::vector<RowTask>& out, int kind, int64_t total, int cap, int64_t first = 0) {
+        int64_t e = first;
         while (e < total) {
             int ne = (int)std::min<int64_t>(cap, total - e);
             task_row_intervals(H, kind, e, ne, n, dB, dE, iv);
@@ -391,7 +432,12 @@ void build_row_tasks(const HostEnum& H, int n, int dB, int dE, int max_rows, int
     emit(xt, ITEM_XD, H.PXD[n], 2 * threads);
     emit(xt, ITEM_XR, H.PXR[n], threads);
 #endif
-    if (with_y) emit(yt, ITEM_Y, H.PY[n], 2 * threads);
+    if (with_y) {
+        emit(yt, ITEM_Y, H.PY[n], 2 * threads);
+        const int nz = dB < dE ? cr_nzd(dB, dE, H.z_first, H.z_last) : 0, nz1 = dB < dE ? H.z_first - dB : 0;
+        emit(yt, ITEM_Z, H.PZ[(size_t)nz1 * n], 2 * threads);                                   // the d below Y's blocks and the d above them: a task's
+        emit(yt, ITEM_Z, H.PZ[(size_t)nz * n], 2 * threads, H.PZ[(size_t)nz1 * n]);              //   d are consecutive matrix rows
+    }
 }
 
 // host half of a plan: everything that needs no CUDA call, so that a helper thread can prepare the next slab's plan
@@ -448,7 +494,11 @@ int upload_plan(qs_ctx* c, const HostPlan& P) {
         if ((r = dev_alloc(c, &c->d_tasks, total + total / 4))) { c->tasks_cap = 0; return r; }
         c->tasks_cap = total + total / 4;
     }
-    if (!c->d_enum && (r = dev_alloc(c, &c->d_enum, (size_t)5 * (c->n + 1)))) return r;
+    const size_t enum_need = (size_t)5 * (c->n + 1) + P.H.PZ.size();
+    if (enum_need > c->enum_cap) {
+        if ((r = dev_alloc(c, &c->d_enum, enum_need + enum_need / 4))) { c->enum_cap = 0; return r; }
+        c->enum_cap = enum_need + enum_need / 4;
+    }
     QS_CUDA(c, cudaStreamSynchronize(c->stream));
     if (!xt.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks, xt.data(), xt.size() * sizeof(RowTask), cudaMemcpyHostToDevice));
     if (!yt.empty()) QS_CUDA(c, cudaMemcpy(c->d_tasks + xt.size(), yt.data(), yt.size() * sizeof(RowTask), cudaMemcpyHostToDevice));
@@ -458,6 +508,8 @@ int upload_plan(qs_ctx* c, const HostPlan& P) {
     QS_CUDA(c, cudaMemcpy(c->d_enum + 2 * np1, P.H.PY.data(), np1 * 8, cudaMemcpyHostToDevice));
     QS_CUDA(c, cudaMemcpy(c->d_enum + 3 * np1, P.H.CD.data(), np1 * 8, cudaMemcpyHostToDevice));
     QS_CUDA(c, cudaMemcpy(c->d_enum + 4 * np1, P.H.PXR.data(), np1 * 8, cudaMemcpyHostToDevice));
+    QS_CUDA(c, cudaMemcpy(c->d_enum + 5 * np1, P.H.PZ.data(), P.H.PZ.size() * 8, cudaMemcpyHostToDevice));
+    c->plan_zF = P.H.z_first; c->plan_zL = P.H.z_last;
     c->plan_dB = P.dB; c->plan_dE = P.dE; c->plan_with_y = P.with_y; c->plan_threads = P.threads; c->plan_nx = (int)xt.size(); c->plan_ny = (int)yt.size(); c->plan_max_rows = P.max_rows;
     c->plan_xcost = P.xcost; c->plan_ycost = P.ycost; ++c->plan_generation;
     return QS_OK;
@@ -512,7 +564,7 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
     a.D = c->d_D; a.order = c->d_order; a.n_class_a = c->d_nA;
     a.tasks = c->d_tasks; a.n_x = c->plan_nx; a.n_y = c->plan_ny;
     const size_t np1 = (size_t)c->n + 1;
-    a.E = EnumTables{c->d_enum, c->d_enum + np1, c->d_enum + 2 * np1, c->d_enum + 3 * np1, c->d_enum + 4 * np1, use_xo_diag(c->n)};
+    a.E = EnumTables{c->d_enum, c->d_enum + np1, c->d_enum + 2 * np1, c->d_enum + 3 * np1, c->d_enum + 4 * np1, c->d_enum + 5 * np1, c->plan_zF, c->plan_zL, use_xo_diag(c->n)};
     a.task_counter = c->d_counter; a.table = table; a.cint_bytes = c->cint_bytes; a.rank_base = rb;
     a.n = c->n; a.n_pad = c->n_pad; a.m = (int)c->m; a.d_begin = dB; a.d_end = dE;
     a.row_bytes = (uint32_t)c->n_pad * 2u;
@@ -1358,7 +1410,11 @@ int qs_count(qs_ctx* ctx) {
     };
     const uint64_t nq = ctx->rank_end - ctx->rank_begin;
     const size_t need = (size_t)nq * 3 * ctx->cint_bytes;
-    if (ctx->auto_mode) {                                     // QS_MODE_AUTO: keep the shard's table resident if it fits beside the matrices
+    // QS_MODE_AUTO: keep the shard's table resident if it fits beside the matrices.  Decided once per (table size, tree count): the
+    // query is an ioctl into the kernel driver, which sleeps on the driver's global lock — on a host whose other GPUs are busy that
+    // took up to 100 ms of a 4.8 ms step (profiles/r02_x_jitter.txt, tools/ctx_switches.py)
+    if (ctx->auto_mode && !(ctx->auto_need == need && ctx->auto_m == ctx->m)) {
+        ctx->auto_need = need; ctx->auto_m = ctx->m;
         size_t free_b = 0, total_b = 0;
         QS_CUDA(ctx, cudaMemGetInfo(&free_b, &total_b));
         size_t limit = free_b + ctx->table_bytes > ((size_t)1 << 30) ? free_b + ctx->table_bytes - ((size_t)1 << 30) : 0;
@@ -1538,9 +1594,9 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
     std::vector<RowTask> xt, yt;
     const int threads = cr_threads_for(n_taxa);
     build_row_tasks(H, n_taxa, dB, dE, max_rows, threads, xt, yt);
-    int64_t items[4] = {0, 0, 0, 0}, slots[4] = {0, 0, 0, 0}, rows = 0, mx = 0, violations = 0, quartets = 0;
-    const int cap[4] = {threads, 2 * threads, 2 * threads, threads};
-    int64_t next_e[4] = {0, 0, 0, 0};
+    int64_t items[ITEM_KINDS] = {}, slots[ITEM_KINDS] = {}, rows = 0, mx = 0, violations = 0, quartets = 0;
+    const int cap[ITEM_KINDS] = {threads, 2 * threads, 2 * threads, threads, 2 * threads};
+    int64_t next_e[ITEM_KINDS] = {};
     auto in_ranges = [](const RowTask& t, int row) {
         for (int k = 0; k < 3; ++k) if (row >= t.rstart[k] && row < t.rstart[k] + t.rcount[k]) return true;
         return false;
@@ -1556,26 +1612,32 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
             for (int i = 0; i < t.ne; ++i) {                                                   // every item's rows are staged, ids are sane
                 int p, q, j, k2;
                 if (t.kind == ITEM_Y) {
-                    cr_decode_y(H.view(), t.e0 + i, n_taxa, dB, p, q, j, k2);
-                    if (!(p >= 1 && p < q && q <= dE - 2 && j < (p + 7) / 8 && k2 * 8 < dE && k2 * 8 + 7 >= cr_dlo(q, dB))) ++violations;
+                    cr_decode_y(H.view(), t.e0 + i, n_taxa, p, q, j, k2);
+                    if (!(p >= 1 && p < q && q <= dE - 2 && j < (p + 7) / 8 && k2 * 8 >= H.z_first && k2 * 8 + 8 <= H.z_last && k2 * 8 + 7 > q)) ++violations;   // whole d-blocks inside Y's range, some d above c
+                } else if (t.kind == ITEM_Z) {
+                    cr_decode_z(H.view(), t.e0 + i, n_taxa, dB, dE, p, q, j, k2);                  // p = d, q = a, blocks j <= k2
+                    if (!(p >= dB && p < dE && (p < H.z_first || p >= H.z_last) && q >= 0 && p - q >= 3 && j >= ((q + 1) >> 3) && j <= k2 && k2 <= ((p - 1) >> 3))) ++violations;
                 } else {
-                    cr_decode_x(t.kind == ITEM_XO ? H.PXO.data() : t.kind == ITEM_XR ? H.PXR.data() : H.PXD.data(), t.kind, H.xo_diag, t.e0 + i, n_taxa, dB, p, q, j);
+                    cr_decode_x(H.prefix(t.kind), t.kind, H.xo_diag, t.e0 + i, n_taxa, dB, p, q, j);
                     if (!(p >= 2 && p < q && q >= dB && q < dE && j < (t.kind == ITEM_XO ? cr_nxo(p, H.xo_diag) : t.kind == ITEM_XR ? cr_nxr(p, H.xo_diag) : cr_nxd(p, H.xo_diag)))) ++violations;
                 }
                 if (!in_ranges(t, p) || !in_ranges(t, q)) ++violations;
             }
         }
-    if (next_e[ITEM_XO] != H.PXO[n_taxa] || next_e[ITEM_XD] != H.PXD[n_taxa] || next_e[ITEM_Y] != H.PY[n_taxa] || next_e[ITEM_XR] != H.PXR[n_taxa]) ++violations;
+    for (int k = 0; k < ITEM_KINDS; ++k) if (next_e[k] != H.total(k)) ++violations;
+    if (dB < dE && !(dB <= H.z_first && H.z_first <= H.z_last && H.z_last <= dE && (H.z_first == dE || H.z_first % 8 == 0) && (H.z_last == dE || H.z_last % 8 == 0))) ++violations;
     quartets = (int64_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB));
     stats[0] = (int64_t)xt.size(); stats[1] = (int64_t)yt.size();
-    stats[2] = items[0]; stats[3] = items[1]; stats[4] = items[2];
-    stats[5] = slots[0]; stats[6] = slots[1]; stats[7] = slots[2];
+    stats[2] = items[0]; stats[3] = items[1]; stats[4] = items[ITEM_Y] + items[ITEM_Z];
+    stats[5] = slots[0]; stats[6] = slots[1]; stats[7] = slots[ITEM_Y] + slots[ITEM_Z];
     stats[8] = rows; stats[9] = mx; stats[10] = violations; stats[11] = quartets;
     stats[12] = items[ITEM_XR]; stats[13] = slots[ITEM_XR];
     // useful compares / issued compares of role X: an XO item issues 128 (8 x 8 quartets x 2 slots), an XD item 64, an XR item 16 per valid b
     int64_t xr_compares = 0;
     for (int cc = 2; cc < n_taxa; ++cc) xr_compares += (int64_t)std::max(0, dE - cr_dlo(cc, dB)) * cr_nxr(cc, H.xo_diag) * 16 * (cc & 7);
     stats[14] = items[ITEM_XO] * 128 + items[ITEM_XD] * 64 + xr_compares;
+    stats[15] = items[ITEM_Z];
+    stats[16] = (items[ITEM_Y] + items[ITEM_Z]) * 64;
     return QS_OK;
 }
 

@@ -12,11 +12,11 @@ from quartetscores_b200.multi import shard_bounds
 
 
 def plan_stats(n, b, e):
-    st = np.zeros(15, np.int64)
+    st = np.zeros(17, np.int64)
     rc = _ffi.load().qs_plan_stats(n, b, e, st.ctypes.data_as(C.POINTER(C.c_int64)))
     assert rc == 0
     keys = ["x_tasks", "y_tasks", "xo_items", "xd_items", "y_items", "xo_slots", "xd_slots", "y_slots", "rows", "max_rows", "violations", "quartets",
-            "xr_items", "xr_slots", "x_compares"]
+            "xr_items", "xr_slots", "x_compares", "z_items", "y_compares"]
     return dict(zip(keys, (int(x) for x in st)))
 
 
@@ -27,7 +27,7 @@ def test_plan_self_check_whole_space(n):
     assert s["quartets"] == comb(n, 4)
     # every quartet lies in exactly one 8x8 block of role X and one of role Y: the blocks must at least cover them
     assert (s["xo_items"] + s["xr_items"]) * 64 + s["xd_items"] * 28 >= comb(n, 4) and s["y_items"] * 64 >= comb(n, 4)
-    assert s["x_compares"] >= 2 * comb(n, 4)
+    assert s["x_compares"] >= 2 * comb(n, 4) and s["y_compares"] >= comb(n, 4)
 
 
 @pytest.mark.parametrize("n,G", [(40, 3), (100, 8), (300, 8)])
@@ -44,6 +44,6 @@ def test_plan_self_check_shards(n, G):
 def test_plan_efficiency_cfg2_shape():
     """BASELINE config 2 shape: tasks are full and most compared lanes are real quartets."""
     s = plan_stats(100, 0, 100)
-    assert s["xo_items"] / s["xo_slots"] > 0.98 and s["y_items"] / s["y_slots"] > 0.98
+    assert s["xo_items"] / s["xo_slots"] > 0.98 and s["y_items"] / s["y_slots"] > 0.95
     useful_x = 2 * s["quartets"] / s["x_compares"]          # the ragged b-block of every (c,d) only runs over its c & 7 valid taxa (XR items)
     assert useful_x > 0.96
