@@ -189,7 +189,10 @@ void shard_bounds(int n, int g, int G, double class_b_fraction, int* d_begin, in
             if (xo > 0) xo = std::max(xo, T / R);
             if (xr > 0) xr = std::max(xr, (0.14 + 0.86 * rg / 8.0) * T / R);
             if (xd > 0) xd = std::max(xd, T / R);
-            A[c + 1] = A[c] + xo + xr + xd;
+            // every (c,d) also brings a matrix row of its own into its tasks' staging: an empirical 31e-6 n^2 items' worth per pair
+            // (the first shard, whose small d hold many pairs with few blocks each, ran 3 % (n = 500) and 5-7 % (n = 1000) over the
+            // others without it: profiles/r02_y_shards.txt, r02_z_bench_cfg4_n8.json)
+            A[c + 1] = A[c] + xo + xr + xd + 31e-6 * n * n;
             double bc = 0;
             for (int bb = 1; bb < c; ++bb) bc += (bb + 7) >> 3;
             B[c + 1] = B[c] + bc;
