@@ -146,8 +146,14 @@ __global__ void __launch_bounds__(256) qs_dist_kernel(DistArgs a) {
 // child whose subtree starts at q+1, and the pair sweep run on all 32 lanes as before.
 constexpr int DW_WARPS = 8;
 constexpr int DW_ARRAYS = 10;    // int16 arrays of max_nodes entries per warp
-__host__ __device__ __forceinline__ size_t dist_warp_smem_per_warp(int max_nodes, int n) {
-    return (size_t)DW_ARRAYS * 2 * ((max_nodes + 7) / 8 * 8) + (size_t)((n + 31) / 32) * 4;
+// SMEM_MATRIX: the warp also keeps the tree's matrix in shared memory and writes it out in 16-byte pieces at the end.  The pair sweep
+// runs in tour order but the matrix is indexed by taxon id, so written straight to global memory every store instruction puts 32
+// two-byte values into scattered columns of one row (5-7 partial sectors each): at cfg2 that, not the arithmetic, was the kernel's
+// time.  Used while the matrix is small (n <= ~110: 8 warps x 25 KB per SM), i.e. exactly where the distance build is a visible
+// part of the step.
+__host__ __device__ __forceinline__ size_t dist_warp_smem_per_warp(int max_nodes, int n, bool smem_matrix = false) {
+    const size_t arrays = ((size_t)DW_ARRAYS * 2 * ((max_nodes + 7) / 8 * 8) + (size_t)((n + 31) / 32) * 4 + 15) & ~(size_t)15;
+    return arrays + (smem_matrix ? (size_t)n * ((n + 7) / 8 * 8) * 2 : 0);
 }
 
 // 16-bit field of a shared int16 array, += v through the 32-bit word that holds it (fields stay < 32768: no carry); returns the old field
@@ -176,11 +182,13 @@ __device__ __forceinline__ void dw_jump(volatile uint32_t* pj, int N, int lane) 
     } while (again);
 }
 
+template <bool SMEM_MATRIX>
 __global__ void __launch_bounds__(32 * DW_WARPS) qs_dist_warp_kernel(DistArgs a) {
     extern __shared__ __align__(16) unsigned char sm_w[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int NP = (a.max_nodes + 7) / 8 * 8, nw = (a.n + 31) / 32;
-    unsigned char* mine = sm_w + (size_t)warp * dist_warp_smem_per_warp(a.max_nodes, a.n);
+    unsigned char* mine = sm_w + (size_t)warp * dist_warp_smem_per_warp(a.max_nodes, a.n, SMEM_MATRIX);
+    __half* const Ms = reinterpret_cast<__half*>(mine + dist_warp_smem_per_warp(a.max_nodes, a.n, false));     // SMEM_MATRIX: this warp's n x n_pad matrix
     int16_t* par = reinterpret_cast<int16_t*>(mine);   // parent
     int16_t* dep = par + NP;                           // depth
     int16_t* cnt = dep + NP;                           // number of children
@@ -267,10 +275,11 @@ __global__ void __launch_bounds__(32 * DW_WARPS) qs_dist_warp_kernel(DistArgs a)
             if (bad) atomicCAS(a.max_dist + 1, 0, bad);
             a.tree_class[t] = (!bad && k == a.n && maxdeg <= 3) ? 0 : 1;
         }
-        __half* Dt = a.D + (size_t)t * a.n * a.n_pad;
+        __half* const Dg = a.D + (size_t)t * a.n * a.n_pad;
+        __half* const Dt = SMEM_MATRIX ? Ms : Dg;             // where the sweep writes
+        const size_t nw16 = (size_t)a.n * a.n_pad / 8;
         if (k < a.n) {                                        // absent taxa / malformed tree: NaN everywhere first (see qs_dist_kernel)
             uint4* w = reinterpret_cast<uint4*>(Dt);
-            const size_t nw16 = (size_t)a.n * a.n_pad / 8;
             for (size_t x = lane; x < nw16; x += 32) w[x] = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
             __syncwarp();
         }
@@ -296,6 +305,12 @@ __global__ void __launch_bounds__(32 * DW_WARPS) qs_dist_warp_kernel(DistArgs a)
                     Dt[(size_t)ltid[j] * a.n_pad + ti] = __int2half_rn(d);
                 }
             }
+        }
+        if (SMEM_MATRIX) {                                    // the finished matrix, 16 bytes per lane and store (the padding columns carry whatever the previous tree left: never read for a result)
+            __syncwarp();
+            const uint4* src = reinterpret_cast<const uint4*>(Ms);
+            uint4* dst = reinterpret_cast<uint4*>(Dg);
+            for (size_t x = lane; x < nw16; x += 32) dst[x] = src[x];
         }
     }
     for (int s = 16; s > 0; s >>= 1) local_max = max(local_max, __shfl_xor_sync(FULL, local_max, s));

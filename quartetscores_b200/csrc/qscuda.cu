@@ -289,13 +289,21 @@ int run_distances(qs_ctx* c) {
     da.node_off = c->d_off; da.parent = c->d_parent; da.leaf_id = c->d_leaf;
     da.m = (int)c->m; da.n = c->n; da.n_pad = c->n_pad; da.max_nodes = c->max_nodes; da.D = c->d_D; da.max_dist = c->d_flags;
     da.tree_class = c->d_class;
-    const size_t warp_smem = dist_warp_smem_per_warp(c->max_nodes, c->n) * DW_WARPS;
+    // the warp kernel keeps the matrix in shared memory while n is small (kernels/dist.cuh); QS_DIST_SMEM_MATRIX = 0 | 1 overrides (tuning)
+    bool smem_matrix = (size_t)c->n * c->n_pad * 2 <= 24 * 1024 && dist_warp_smem_per_warp(c->max_nodes, c->n, true) * DW_WARPS + 1024 <= (size_t)c->smem_optin;
+    if (const char* env = getenv("QS_DIST_SMEM_MATRIX")) smem_matrix = smem_matrix && atoi(env) != 0;
+    const size_t warp_smem = dist_warp_smem_per_warp(c->max_nodes, c->n, smem_matrix) * DW_WARPS;
     if (c->max_nodes <= 2048 && c->n <= 32767 && warp_smem <= (size_t)c->smem_optin) {
         // small trees: one warp per tree, as many trees in flight as shared memory allows
-        QS_CUDA(c, cudaFuncSetAttribute(qs_dist_warp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
         int per_sm = std::max(1, std::min(8, (int)((size_t)c->smem_optin / (warp_smem + 1024))));
         int grid = (int)std::min<int64_t>((c->m + DW_WARPS - 1) / DW_WARPS, (int64_t)c->num_sms * per_sm);
-        qs_dist_warp_kernel<<<grid, 32 * DW_WARPS, warp_smem, c->stream>>>(da);
+        if (smem_matrix) {
+            QS_CUDA(c, cudaFuncSetAttribute(qs_dist_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
+            qs_dist_warp_kernel<true><<<grid, 32 * DW_WARPS, warp_smem, c->stream>>>(da);
+        } else {
+            QS_CUDA(c, cudaFuncSetAttribute(qs_dist_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)warp_smem));
+            qs_dist_warp_kernel<false><<<grid, 32 * DW_WARPS, warp_smem, c->stream>>>(da);
+        }
     } else {
         size_t smem = (size_t)8 * 4 * c->max_nodes + (size_t)((c->n + 31) / 32) * 4;
         if (smem > (size_t)c->smem_optin) QS_FAIL(c, QS_E_UNSUPPORTED, "gene tree with %d nodes exceeds the distance kernel's shared-memory budget", c->max_nodes);
@@ -1597,7 +1605,7 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
     std::vector<RowTask> xt, yt;
     const int threads = cr_threads_for(n_taxa);
     build_row_tasks(H, n_taxa, dB, dE, max_rows, threads, xt, yt);
-    int64_t items[ITEM_KINDS] = {}, slots[ITEM_KINDS] = {}, rows = 0, mx = 0, violations = 0, quartets = 0;
+    int64_t items[ITEM_KINDS] = {}, slots[ITEM_KINDS] = {}, rows = 0, mx = 0, violations = 0, quartets = 0, slot0_covered = 0;
     const int cap[ITEM_KINDS] = {threads, 2 * threads, 2 * threads, threads, 2 * threads};
     int64_t next_e[ITEM_KINDS] = {};
     auto in_ranges = [](const RowTask& t, int row) {
@@ -1617,9 +1625,13 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
                 if (t.kind == ITEM_Y) {
                     cr_decode_y(H.view(), t.e0 + i, n_taxa, p, q, j, k2);
                     if (!(p >= 1 && p < q && q <= dE - 2 && j < (p + 7) / 8 && k2 * 8 >= H.z_first && k2 * 8 + 8 <= H.z_last && k2 * 8 + 7 > q)) ++violations;   // whole d-blocks inside Y's range, some d above c
+                    // the quartets the kernel's flush keeps of this item: a < b in the a-block, d > c in the d-block (count_rows.cuh)
+                    slot0_covered += (int64_t)std::max(0, std::min(8, p - j * 8)) * std::max(0, k2 * 8 + 8 - std::max(k2 * 8, q + 1));
                 } else if (t.kind == ITEM_Z) {
                     cr_decode_z(H.view(), t.e0 + i, n_taxa, dB, dE, p, q, j, k2);                  // p = d, q = a, blocks j <= k2
                     if (!(p >= dB && p < dE && (p < H.z_first || p >= H.z_last) && q >= 0 && p - q >= 3 && j >= ((q + 1) >> 3) && j <= k2 && k2 <= ((p - 1) >> 3))) ++violations;
+                    for (int cc = k2 * 8; cc < k2 * 8 + 8 && cc < p; ++cc)                         // the flush keeps a < b < c < d
+                        slot0_covered += std::max(0, std::min(j * 8 + 8, cc) - std::max(j * 8, q + 1));
                 } else {
                     cr_decode_x(H.prefix(t.kind), t.kind, H.xo_diag, t.e0 + i, n_taxa, dB, p, q, j);
                     if (!(p >= 2 && p < q && q >= dB && q < dE && j < (t.kind == ITEM_XO ? cr_nxo(p, H.xo_diag) : t.kind == ITEM_XR ? cr_nxr(p, H.xo_diag) : cr_nxd(p, H.xo_diag)))) ++violations;
@@ -1628,6 +1640,7 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
             }
         }
     for (int k = 0; k < ITEM_KINDS; ++k) if (next_e[k] != H.total(k)) ++violations;
+    if (slot0_covered != (int64_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB))) ++violations;      // roles Y and Z together hold every quartet of the range exactly once
     if (dB < dE && !(dB <= H.z_first && H.z_first <= H.z_last && H.z_last <= dE && (H.z_first == dE || H.z_first % 8 == 0) && (H.z_last == dE || H.z_last % 8 == 0))) ++violations;
     quartets = (int64_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB));
     stats[0] = (int64_t)xt.size(); stats[1] = (int64_t)yt.size();

@@ -1,6 +1,7 @@
 """Host logic of the counting kernel (CPU only): the task table built by libqscuda (qs_plan_stats runs the
-builder and its self-check: tasks tile every item enumeration exactly once, every item decodes to sane taxon ids
-and its two matrix rows lie inside the task's staged row ranges)."""
+builder and its self-check: tasks tile every item enumeration exactly once, every item decodes to sane taxon ids,
+its two matrix rows lie inside the task's staged row ranges, and the quartets that the items of roles Y and Z keep
+after their flush masks add up to exactly the quartets of the range)."""
 import ctypes as C
 from math import comb
 
@@ -47,3 +48,23 @@ def test_plan_efficiency_cfg2_shape():
     assert s["xo_items"] / s["xo_slots"] > 0.98 and s["y_items"] / s["y_slots"] > 0.95
     useful_x = 2 * s["quartets"] / s["x_compares"]          # the ragged b-block of every (c,d) only runs over its c & 7 valid taxa (XR items)
     assert useful_x > 0.96
+
+
+def test_plan_self_check_random_ranges():
+    """Arbitrary d-ranges (slabs, shards of any width): role Y owns whole d-blocks, role Z the d of the cut blocks or — for a
+    range with few whole blocks — every d; the plan's self-check covers the split, the decoding of every item and its rows."""
+    rng = np.random.default_rng(7)
+    seen_all_z = seen_both = 0
+    for _ in range(40):
+        n = int(rng.integers(8, 260))
+        b = int(rng.integers(0, n - 1))
+        e = int(rng.integers(b + 1, n + 1))
+        s = plan_stats(n, b, e)
+        lo = max(3, b)
+        assert s["violations"] == 0, (n, b, e, s)
+        assert s["quartets"] == (comb(e, 4) - comb(lo, 4) if e > lo else 0)
+        if e > lo:
+            assert s["y_compares"] >= s["quartets"]
+            seen_all_z += s["z_items"] == s["y_items"]
+            seen_both += 0 < s["z_items"] < s["y_items"]
+    assert seen_all_z >= 5 and seen_both >= 5
