@@ -149,8 +149,9 @@ constexpr int DW_ARRAYS = 10;    // int16 arrays of max_nodes entries per warp
 // SMEM_MATRIX: the warp also keeps the tree's matrix in shared memory and writes it out in 16-byte pieces at the end.  The pair sweep
 // runs in tour order but the matrix is indexed by taxon id, so written straight to global memory every store instruction puts 32
 // two-byte values into scattered columns of one row (5-7 partial sectors each): at cfg2 that, not the arithmetic, was the kernel's
-// time.  Used while the matrix is small (n <= ~110: 8 warps x 25 KB per SM), i.e. exactly where the distance build is a visible
-// part of the step.
+// time.  Only possible while the matrix is small (n <= ~110: 8 warps x 25 KB per SM) — and measured SLOWER there (0.47 against 0.27 ms at
+// cfg2, profiles/r02_d_*): with 8 warps per SM instead of 48 the latency chains of the per-tree passes are no longer hidden.  Opt-in
+// (QS_DIST_SMEM_MATRIX=1), kept for the record and for smaller matrices.
 __host__ __device__ __forceinline__ size_t dist_warp_smem_per_warp(int max_nodes, int n, bool smem_matrix = false) {
     const size_t arrays = ((size_t)DW_ARRAYS * 2 * ((max_nodes + 7) / 8 * 8) + (size_t)((n + 31) / 32) * 4 + 15) & ~(size_t)15;
     return arrays + (smem_matrix ? (size_t)n * ((n + 7) / 8 * 8) * 2 : 0);

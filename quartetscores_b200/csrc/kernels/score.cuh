@@ -196,8 +196,15 @@ __host__ __device__ constexpr uint32_t scan_chunk_bytes(int threads) { return (u
 __host__ __device__ __forceinline__ size_t scan_acc_bytes(int n, int levels, bool carry) {
     return (size_t)(2 * n + q4_slots(levels)) * (carry ? 32 : 20) + (size_t)((n + 7) / 8 * 8) * 2 + (size_t)levels * 4 + 64;
 }
-__host__ __device__ __forceinline__ size_t scan_ring_bytes(int threads, int cint_bytes) {       // barriers | staging ring | tau table
-    return 128 + (cint_bytes == 2 ? (size_t)scan_stages(threads) * scan_chunk_bytes(threads) : 0) + (1024 + 8) * 4;
+// Candidates for a pair's minimum are not evaluated where they are found: a warp that stops for the fp64 evaluation and its global
+// atomics (~5 dependent round trips) holds up its whole CTA at the item's barrier — at n = 100, where an item is a few thousand
+// entries, that was most of the kernel's time (profiles/r02_d_scan_cfg2_*).  Each warp queues them in shared memory and evaluates a
+// batch with all lanes at once; the slot's bound is lowered at once with the estimate's upper end, which is all the filter needs.
+struct ScanCand { uint32_t c0, c1, c2, uv; int key; };            // counts, u | v << 16, slot * 2 + (reference topology is slot 2)
+__host__ __device__ constexpr int scan_queue_cap(int threads) { return threads >= 900 ? 16 : 32; }
+__host__ __device__ constexpr size_t scan_queue_bytes(int threads) { return (size_t)(threads / 32) * ((size_t)scan_queue_cap(threads) * sizeof(ScanCand) + 16); }
+__host__ __device__ __forceinline__ size_t scan_ring_bytes(int threads, int cint_bytes) {       // barriers | staging ring | tau table | candidate queues
+    return 128 + (cint_bytes == 2 ? (size_t)scan_stages(threads) * scan_chunk_bytes(threads) : 0) + (1024 + 8) * 4 + scan_queue_bytes(threads);
 }
 
 __device__ __forceinline__ int bound_from_score(long long sc) {
@@ -273,6 +280,11 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS <= 512 ? 2 : 1)) qs_sca
     uint16_t* acc_pq = reinterpret_cast<uint16_t*>(acc_tau + n_acc);                              // [n] q of the accP key (p, q)
     int* s_anc = reinterpret_cast<int*>(acc_pq + (n + 7) / 8 * 8);                                // [LV] ancestors of leaf c below r
     float* s_tau = reinterpret_cast<float*>(sm_scan + 128 + (RING ? (size_t)STAGES * CHUNK_BYTES : 0));   // [QS_TAU_STEPS + 1] (always shared memory)
+    constexpr int QCAP = scan_queue_cap(THREADS);
+    unsigned char* wq_base = reinterpret_cast<unsigned char*>(s_tau) + (1024 + 8) * 4 + (size_t)(threadIdx.x >> 5 < WARPS ? threadIdx.x >> 5 : 0) * (QCAP * sizeof(ScanCand) + 16);
+    int* wq_cnt = reinterpret_cast<int*>(wq_base);                                                // this warp's queue of candidates: count,
+    ScanCand* wq = reinterpret_cast<ScanCand*>(wq_base + 16);                                     //   entries
+    if ((tid & 31) == 0 && tid < THREADS) *wq_cnt = 0;
     const int shift = a.count_scale == 2 ? 1 : 0;
     const uint32_t mask32 = (uint32_t)a.cint_mask;                    // (counts are <= m < 2^31 whatever CINT is; the scaled value is masked to CINT)
     const CINT* table = reinterpret_cast<const CINT*>(a.table);
@@ -300,6 +312,21 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS <= 512 ? 2 : 1)) qs_sca
         const int bb = bound_from_score(score);
         acc_b[slot] = bb;
         acc_tau[slot] = float_to_ordered(qs_tau_lookup(s_tau, ordered_to_float(bb)));
+    };
+    auto drain = [&]() {                                          // consumer warps, all lanes: evaluate the queued candidates, 32 at a time
+        __syncwarp();
+        const int cnt = min(*reinterpret_cast<volatile int*>(wq_cnt), QCAP);
+        for (int base = 0; base < cnt; base += 32) {
+            const int e = base + (tid & 31);
+            if (e < cnt) {
+                const ScanCand cd = wq[e];
+                const int sl = cd.key >> 1;
+                scan_cold(a.pair_sums, a.pair_best, a.pair_score, a.I, a.bifurcating, (cd.key & 1) ? 2 : 0, cd.c0, cd.c1, cd.c2, (int)(cd.uv & 0xffffu), (int)(cd.uv >> 16), acc_b + sl, acc_tau + sl, s_tau, false);
+            }
+        }
+        __syncwarp();
+        if ((tid & 31) == 0) *wq_cnt = 0;
+        __syncwarp();
     };
     for (int j = tid; j <= QS_TAU_STEPS; j += THREADS + 32) s_tau[j] = qs_tau_of_bound((float)j / (float)QS_TAU_STEPS);
 
@@ -452,7 +479,13 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS <= 512 ? 2 : 1)) qs_sca
                                     const int p = (int)(pd[i] & 0xffffu), q = (int)(qd[i] & 0xffffu);
                                     int u, v;
                                     if (slot[i] < n) { u = slot[i]; v = r; } else if (slot[i] < 2 * n) { u = p; v = q; } else { u = q; v = p; }
-                                    scan_cold(a.pair_sums, a.pair_best, a.pair_score, a.I, a.bifurcating, rs2 ? 2 : 0, c0, c1, c2, u, v, acc_b + slot[i], acc_tau + slot[i], s_tau, false);
+                                    // its score is <= ub: whoever cannot beat ub needs no look (the candidate itself still passes: est - eps < ub)
+                                    const float ub = exact ? est : est + QS_EST_EPS;
+                                    atomicMin(acc_b + slot[i], float_to_ordered(ub));
+                                    atomicMin(acc_tau + slot[i], float_to_ordered(qs_tau_lookup(s_tau, ub)));
+                                    const int qi = atomicAdd(wq_cnt, 1);
+                                    if (qi < QCAP) wq[qi] = ScanCand{c0, c1, c2, (uint32_t)u | ((uint32_t)v << 16), slot[i] * 2 + (rs2 ? 1 : 0)};
+                                    else scan_cold(a.pair_sums, a.pair_best, a.pair_score, a.I, a.bifurcating, rs2 ? 2 : 0, c0, c1, c2, u, v, acc_b + slot[i], acc_tau + slot[i], s_tau, false);     // queue full
                                 }
                             }
                         } else {                                  // slot -2: key (q, p) deeper than accQ reaches: sums and selection in global memory
@@ -464,8 +497,11 @@ __global__ void __launch_bounds__(THREADS + 32, (THREADS <= 512 ? 2 : 1)) qs_sca
                     __syncwarp();
                     if ((tid & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&empty[stage])) : "memory");
                 }
+                __syncwarp();
+                if (*reinterpret_cast<volatile int*>(wq_cnt) >= QCAP / 2) drain();       // (after the hand-over: the next chunk lands meanwhile)
             }
         }
+        drain();                                                 // the slots' bounds belong to this item
         }
         __syncthreads();
         // ---- flush the CTA's accumulators: one global atomic per touched key ----

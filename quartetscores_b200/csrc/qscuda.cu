@@ -289,9 +289,11 @@ int run_distances(qs_ctx* c) {
     da.node_off = c->d_off; da.parent = c->d_parent; da.leaf_id = c->d_leaf;
     da.m = (int)c->m; da.n = c->n; da.n_pad = c->n_pad; da.max_nodes = c->max_nodes; da.D = c->d_D; da.max_dist = c->d_flags;
     da.tree_class = c->d_class;
-    // the warp kernel keeps the matrix in shared memory while n is small (kernels/dist.cuh); QS_DIST_SMEM_MATRIX = 0 | 1 overrides (tuning)
+    // QS_DIST_SMEM_MATRIX=1: the warp kernel keeps the matrix of a small tree in shared memory (kernels/dist.cuh).  Measured slower
+    // (0.47 against 0.27 ms at cfg2: 8 warps per SM instead of 48), so it stays an opt-in
     bool smem_matrix = (size_t)c->n * c->n_pad * 2 <= 24 * 1024 && dist_warp_smem_per_warp(c->max_nodes, c->n, true) * DW_WARPS + 1024 <= (size_t)c->smem_optin;
     if (const char* env = getenv("QS_DIST_SMEM_MATRIX")) smem_matrix = smem_matrix && atoi(env) != 0;
+    else smem_matrix = false;
     const size_t warp_smem = dist_warp_smem_per_warp(c->max_nodes, c->n, smem_matrix) * DW_WARPS;
     if (c->max_nodes <= 2048 && c->n <= 32767 && warp_smem <= (size_t)c->smem_optin) {
         // small trees: one warp per tree, as many trees in flight as shared memory allows
