@@ -132,6 +132,69 @@ def test_big_trees_unary_chains_counts_and_distances():
             assert np.array_equal(ctx.get_distances(t), D), f"tree {t}"
 
 
+def _renumber_breadth_first(flat, rng):
+    """the same trees with their nodes numbered level by level and the children of a node in random order: parent[i] < i still
+    holds, but the numbering is no depth-first preorder (the C ABI promises nothing else, include/qscuda.h)"""
+    off, par, leaf = [0], [], []
+    for t in range(flat.n_trees):
+        o0, o1 = flat.node_offsets[t], flat.node_offsets[t + 1]
+        p, l = flat.parent[o0:o1], flat.leaf_lookup_id[o0:o1]
+        kids = [[] for _ in range(len(p))]
+        for i in range(1, len(p)):
+            kids[p[i]].append(i)
+        order, new_index = [0], {0: 0}
+        for v in order:
+            ch = list(kids[v])
+            rng.shuffle(ch)
+            for c in ch:
+                new_index[c] = len(order)
+                order.append(c)
+        par.extend(-1 if p[v] < 0 else new_index[p[v]] for v in order)
+        leaf.extend(int(l[v]) for v in order)
+        off.append(len(par))
+    return FlatTrees(np.asarray(off, np.int64), np.asarray(par, np.int32), np.asarray(leaf, np.int32))
+
+
+def _caterpillar(order):
+    """parent / leaf arrays of the caterpillar on the taxa in `order`: a chain of inner nodes first, then the leaves"""
+    k = len(order)
+    par = [-1] + list(range(0, k - 3))                  # inner chain 0 .. k-3
+    leaf = [-1] * (k - 2)
+    for j, tx in enumerate(order):
+        par.append(min(max(j - 1, 0), k - 3))            # two leaves at each end, one on every node in between
+        leaf.append(int(tx))
+    return par, leaf
+
+
+def test_warp_distance_kernel_node_orders_and_deep_trees():
+    """The warp-per-tree distance kernel (trees of <= 2048 nodes) computes depths and tour positions by pointer jumping and
+    shared-memory atomics under the only promise parent[i] < i: breadth-first numberings with shuffled children, caterpillars (their
+    leaves are deep: the serial leaf-count pass), a star, and unary chains — matrices against the oracle, then the whole table."""
+    n = 120
+    rng = np.random.default_rng(17)
+    s = SyntheticInput(n, 6, 91, k_max=25, p_missing=0.05, p_contract=0.05, want_newick=False)
+    ref = flatten_reference(parse_newick(s.ref_newick))
+    trees = [_renumber_breadth_first(s.flat, rng)]
+    off, par, leaf = [0], [], []
+    for _ in range(3):                                    # caterpillars on a random 110 of the 120 taxa
+        p, l = _caterpillar(rng.permutation(n)[:110])
+        par += p; leaf += l; off.append(len(par))
+    par += [-1] + [0] * n; leaf += [-1] + list(range(n)); off.append(len(par))       # a star: every quartet unresolved
+    trees.append(FlatTrees(np.asarray(off, np.int64), np.asarray(par, np.int32), np.asarray(leaf, np.int32)))
+    small = SyntheticInput(n, 2, 92, k_max=10, want_newick=False)
+    trees.append(_with_unary_chains(small.flat, 7))       # ~1,100 nodes per tree
+    flat = FlatTrees(np.concatenate([[0]] + [f.node_offsets[1:] + sum(int(g.node_offsets[-1]) for g in trees[:i]) for i, f in enumerate(trees)]).astype(np.int64),
+                     np.concatenate([f.parent for f in trees]).astype(np.int32), np.concatenate([f.leaf_lookup_id for f in trees]).astype(np.int32))
+    assert int(np.diff(flat.node_offsets).max()) <= 2048
+    want = O.count_fourpoint(n, flat)
+    with _ctx(ref, flat, 1) as ctx:
+        o = flat.node_offsets
+        for t in range(flat.n_trees):
+            D, _ = O.distance_matrix(flat.parent[o[t]:o[t + 1]], flat.leaf_lookup_id[o[t]:o[t + 1]], n)
+            assert np.array_equal(ctx.get_distances(t), D), f"tree {t}"
+        assert np.array_equal(ctx.get_counts().astype(np.uint32), want)
+
+
 def test_big_trees_1100_taxa_distances_and_sampled_counts():
     """1,100 taxa: ~2,200 nodes per gene tree -> qs_dist_kernel; matrices vs the oracle, and the last shard's first/last entries"""
     n = 1100
