@@ -343,9 +343,9 @@ int use_xo_diag(int n) { return n > 160 ? 1 : 0; }
 // against 396 ms with Z for every d, profiles/r02_x_z_everywhere.txt) — its 8 consecutive a are neighbours in the table, Z's flush scatters
 void z_split(int dB, int dE, int* z_first, int* z_last) {
     int zf = std::min(dE, (dB + 7) & ~7), zl = std::max(zf, dE & ~7);
-    int min_blocks = 8, max_span = 80;
-    if (const char* env = getenv("QS_Z_MIN_BLOCKS")) min_blocks = atoi(env);         // tuning hooks
-    if (const char* env = getenv("QS_Z_MAX_SPAN")) max_span = atoi(env);
+    // (tuning hooks, read once: shard_bounds calls this ~60 n times)
+    static const int min_blocks = [] { const char* env = getenv("QS_Z_MIN_BLOCKS"); return env ? atoi(env) : 8; }();
+    static const int max_span = [] { const char* env = getenv("QS_Z_MAX_SPAN"); return env ? atoi(env) : 80; }();
     if (((zl - zf) >> 3) < min_blocks && dE - dB <= max_span) zf = zl = dE;
     *z_first = zf; *z_last = zl;
 }
