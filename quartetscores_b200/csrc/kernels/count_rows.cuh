@@ -15,10 +15,11 @@
 // 0 = ab|cd, 1 = ac|bd, 2 = ad|bc (src/quartet_lookup_table.hpp:87-111):
 //   role X, pair (c,d) fixed:  G_cd(a) > G_cd(b) -> slot 1,   G_cd(a) < G_cd(b) -> slot 2
 //   role Y, pair (b,c) fixed:  G_bc(a) > G_bc(d) -> slot 0
+//   role Z, pair (a,d) fixed:  G_ad(b) > G_ad(c) -> slot 0   (the same compare with the other two taxa held fixed; Y and Z share slot 0)
 // A missing taxon makes D = NaN in its row/column, G = NaN, and every ordered compare false, so such
 // (quartet, tree) pairs count nothing — exactly the reference, where absent taxa are never enumerated.
 //
-// Fully resolved trees need no role Y.  The distance kernel classifies every gene tree: class A = all n
+// Fully resolved trees need no role Y / Z.  The distance kernel classifies every gene tree: class A = all n
 // taxa present and no node of degree > 3, i.e. every quartet is resolved in it, so
 // slot0 + slot1 + slot2 = 1 per tree and slot 0 = |A| - slot1_A - slot2_A.  Class-A trees (first in the
 // class-sorted order[]) only run role X: 2 compares per quartet x tree instead of 3.
@@ -27,7 +28,10 @@
 //   XO  (c; d; a-block ia < b-block ib): G(a)>G(b) and G(a)<G(b)                               1 item / thread
 //   XD  (c; d; diagonal block i, a and b in the same block): all ordered pairs, G(x)>G(y) only;
 //       x<y gives slot 1 of (x,y), x>y gives slot 2 of (y,x) — half the cost of a full block   2 items / thread
-//   Y   (b; c; d-block; a-block): G(a)>G(d)                                                    2 items / thread
+//   XR  (c; d; a-block x the ragged last b-block of c): as XO over the c mod 8 valid b only           1 item / thread
+//   Y   (b; c; whole d-block inside the range; a-block): G(a)>G(d)                                    2 items / thread
+//   Z   (d; a; b-block <= c-block between a and d): G(b)>G(c), for the d whose block of 8 the shard's range cuts
+//       (and every d of a narrow range): one d per item, so no padding in d                           2 items / thread
 // so a thread always carries 64 packed counter registers and issues 64 HSET2 + 64 IMAD.IADD per tree.  A task
 // is a run of up to THREADS (512 or 256, see below) thread-items of one kind; consecutive items share matrix rows, and the host records
 // the rows a task touches as at most three contiguous row ranges.  Only those rows are staged per tree
