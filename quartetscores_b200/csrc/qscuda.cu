@@ -594,7 +594,7 @@ int run_count_rows(qs_ctx* c, int dB, int dE, void* table, const HostPlan* ready
     // Tree chunks: a task runs over <= QS_MAX_CHUNK_TREES = 4096 trees (the chunk's tree ids live in shared memory).  Tasks differ in
     // length (ragged-block tasks are shorter) and there are only a few per SM, so how well the last ones fill the machine decides
     // several per cent: the chunk count is the one whose greedy schedule — tasks handed out in table order to the first free
-    // CTA, exactly what the kernel's atomic counter does — ends earliest, with ~40 trees' worth of flush and pipeline start per task (measured: 13 us per task at cfg2, profiles/r02_j_variants.txt).
+    // CTA, exactly what the kernel's atomic counter does — ends earliest, with ~40 trees' worth of flush and pipeline start per task (measured: 13 us per task at cfg2, profiles/r02_j_count_variants.txt).
     // The class split is the previous run's (a hint: it only affects the choice, never the result).
     const int64_t mA_hint = c->counted_once ? std::min<int64_t>(c->n_class_a, c->m) : 0, mB_hint = c->m - mA_hint;
     const int64_t k_min = std::max<int64_t>(1, (c->m + QS_MAX_CHUNK_TREES - 1) / QS_MAX_CHUNK_TREES);
