@@ -46,9 +46,10 @@ enum {
 enum {
     QS_MODE_TABLE = 0,      /* keep the (sharded) count table resident: fast + qs_get_counts / qs_raw_qic possible */
     QS_MODE_TABLE_FREE = 1, /* -s / savemem analogue: counts are scored as they are produced, no table */
-    QS_MODE_AUTO = 2        /* the reference constructor's memory policy (QuartetScoreComputer.hpp:724-745) applied to HBM: every
+    QS_MODE_AUTO = 2        /* the reference constructor's memory policy (QuartetScoreComputer.hpp:724-745) applied to HBM:
                              * qs_count keeps the shard's table resident if it fits this device beside the distance matrices
-                             * and falls back to table-free otherwise, instead of failing with QS_E_MEMORY */
+                             * and falls back to table-free otherwise, instead of failing with QS_E_MEMORY (decided when the
+                             * table size or the number of trees changes, not on every call) */
 };
 
 /* device for qs_create: a host-only context.  It makes no CUDA call and supports only the host-side pieces
