@@ -177,8 +177,8 @@ int qs_table_resident(const qs_ctx* ctx, int* resident);
 /* Diagnostics of the counting kernel's host-built task table for the quartets with s3 in [s3_begin, s3_end)
  * (pure host function, no context, no GPU).  stats[17] = {X tasks, Y tasks, XO items, XD items, Y + Z items,
  * XO item slots, XD item slots, Y + Z item slots, staged rows summed over tasks, max rows of a task,
- * self-check violations (must be 0: tasks tile each enumeration, every item's rows are staged, the items of roles Y and Z
- * together keep every quartet of the range exactly once), quartets,
+ * self-check violations (must be 0: tasks tile each enumeration, every item's rows are staged, the items of role X keep
+ * every quartet of the range exactly once, and so do those of roles Y and Z together), quartets,
  * XR items, XR item slots, compares issued by role X per tree (2 x quartets of them are useful), Z items (role-Y work
  * on the d whose block of 8 the range cuts), compares issued by roles Y and Z per tree (1 x quartets of them are useful)}. */
 int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats);

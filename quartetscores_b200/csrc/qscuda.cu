@@ -1607,7 +1607,7 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
     std::vector<RowTask> xt, yt;
     const int threads = cr_threads_for(n_taxa);
     build_row_tasks(H, n_taxa, dB, dE, max_rows, threads, xt, yt);
-    int64_t items[ITEM_KINDS] = {}, slots[ITEM_KINDS] = {}, rows = 0, mx = 0, violations = 0, quartets = 0, slot0_covered = 0;
+    int64_t items[ITEM_KINDS] = {}, slots[ITEM_KINDS] = {}, rows = 0, mx = 0, violations = 0, quartets = 0, slot0_covered = 0, slot12_covered = 0;
     const int cap[ITEM_KINDS] = {threads, 2 * threads, 2 * threads, threads, 2 * threads};
     int64_t next_e[ITEM_KINDS] = {};
     auto in_ranges = [](const RowTask& t, int row) {
@@ -1637,12 +1637,19 @@ int qs_plan_stats(int n_taxa, int s3_begin, int s3_end, int64_t* stats) {
                 } else {
                     cr_decode_x(H.prefix(t.kind), t.kind, H.xo_diag, t.e0 + i, n_taxa, dB, p, q, j);
                     if (!(p >= 2 && p < q && q >= dB && q < dE && j < (t.kind == ITEM_XO ? cr_nxo(p, H.xo_diag) : t.kind == ITEM_XR ? cr_nxr(p, H.xo_diag) : cr_nxd(p, H.xo_diag)))) ++violations;
+                    // the pairs a < b < c the kernel's flush keeps of this item (count_rows.cuh): p = c here
+                    const int nf = cr_nfull(p), rg = p - nf * 8;
+                    auto pairs_in = [](int k) { return k * (k - 1) / 2; };
+                    if (t.kind == ITEM_XO) slot12_covered += j < nf * (nf - 1) / 2 ? 64 : pairs_in(8);              // a-block below a full b-block / a full diagonal block
+                    else if (t.kind == ITEM_XR) slot12_covered += j < nf ? 8 * rg : pairs_in(rg);                   // ... the ragged b-block / the ragged diagonal block
+                    else slot12_covered += pairs_in(std::min(8, p - j * 8));                                         // XD: diagonal block j
                 }
                 if (!in_ranges(t, p) || !in_ranges(t, q)) ++violations;
             }
         }
     for (int k = 0; k < ITEM_KINDS; ++k) if (next_e[k] != H.total(k)) ++violations;
     if (slot0_covered != (int64_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB))) ++violations;      // roles Y and Z together hold every quartet of the range exactly once
+    if (slot12_covered != (int64_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB))) ++violations;     // ... and so do the role-X kinds
     if (dB < dE && !(dB <= H.z_first && H.z_first <= H.z_last && H.z_last <= dE && (H.z_first == dE || H.z_first % 8 == 0) && (H.z_last == dE || H.z_last % 8 == 0))) ++violations;
     quartets = (int64_t)(binom4((uint64_t)dE) - binom4((uint64_t)dB));
     stats[0] = (int64_t)xt.size(); stats[1] = (int64_t)yt.size();

@@ -1,7 +1,7 @@
 """Host logic of the counting kernel (CPU only): the task table built by libqscuda (qs_plan_stats runs the
 builder and its self-check: tasks tile every item enumeration exactly once, every item decodes to sane taxon ids,
-its two matrix rows lie inside the task's staged row ranges, and the quartets that the items of roles Y and Z keep
-after their flush masks add up to exactly the quartets of the range)."""
+its two matrix rows lie inside the task's staged row ranges, and the quartets that the items keep after their flush
+masks add up to exactly the quartets of the range — once over the role-X kinds, once over roles Y and Z)."""
 import ctypes as C
 from math import comb
 
