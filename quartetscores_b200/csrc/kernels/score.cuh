@@ -53,9 +53,6 @@ struct ScoreArgs {
     uint64_t rank_base;
     const uint32_t* lcapd;           // [n][n] inner index of lca(leaf x, leaf y) | its depth << 16 (one load instead of two dependent ones)
     const uint16_t* idepth;          // [I] depth of an inner node (by inner index)
-    const uint32_t* run_off;         // [n+1] row b of lca[][] restricted to a < b, run-length encoded: runs run_off[b] .. run_off[b+1]
-    const uint32_t* run_end;         //   exclusive end (in a) of the run
-    const uint32_t* run_pd;          //   inner index of lca(a,b) | its depth << 16
     const int32_t* inner_parent;     // [I] inner index of the parent inner node, -1 for the root
     const int32_t* leaf_parent;      // [n] inner index of the parent of leaf x
     const int32_t* inner_gap;        // [I] first gap of the inner node = a leaf below its first child (n + k for single-child nodes)

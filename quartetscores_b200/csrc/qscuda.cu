@@ -45,7 +45,6 @@ struct HostRef {
     std::vector<uint16_t> lca;          // [n][n] inner index
     std::vector<uint16_t> idepth;       // [I]
     // scan kernel (kernels/score.cuh): rows of lca[][] run-length encoded, parents in inner-index space
-    std::vector<uint32_t> run_off, run_end, run_pd;
     std::vector<int32_t> inner_parent, leaf_parent, inner_gap;
 };
 
@@ -69,7 +68,6 @@ struct qs_ctx {
     HostRef ref;
     uint32_t* d_lcapd = nullptr;          // [n][n] lca inner index | depth << 16
     uint16_t* d_idepth = nullptr;
-    uint32_t *d_run_off = nullptr, *d_run_end = nullptr, *d_run_pd = nullptr;
     int32_t *d_inner_parent = nullptr, *d_leaf_parent = nullptr, *d_inner_gap = nullptr;
     int32_t *d_inner_node = nullptr, *d_node_parent = nullptr, *d_node_depth = nullptr, *d_node_edge = nullptr, *d_node_inner = nullptr;
     long long* d_edge = nullptr;          // [4][E] edge minima / arg-minima of the per-edge reduction
@@ -257,7 +255,7 @@ uint64_t cint_mask(int bytes) { return bytes >= 8 ? ~0ull : ((1ull << (8 * bytes
 
 void free_all(qs_ctx* c) {
     cudaFree(c->d_lcapd); cudaFree(c->d_idepth);
-    cudaFree(c->d_run_off); cudaFree(c->d_run_end); cudaFree(c->d_run_pd); cudaFree(c->d_inner_parent); cudaFree(c->d_leaf_parent); cudaFree(c->d_inner_gap);
+    cudaFree(c->d_inner_parent); cudaFree(c->d_leaf_parent); cudaFree(c->d_inner_gap);
     cudaFree(c->d_inner_node); cudaFree(c->d_node_parent); cudaFree(c->d_node_depth); cudaFree(c->d_node_edge); cudaFree(c->d_node_inner);
     cudaFree(c->d_edge); cudaFree(c->d_edge_out); cudaFree(c->d_scan_scratch); cudaFree(c->d_scan_counter); cudaFree(c->d_scan_items);
     cudaFree(c->d_off); cudaFree(c->d_parent); cudaFree(c->d_leaf);
@@ -744,21 +742,6 @@ int build_reference(qs_ctx* c, int n_nodes, const int32_t* parent, const int32_t
                 for (int x = lo[c1]; x < hi[c1]; ++x)
                     for (int y = lo[c2]; y < hi[c2]; ++y) { R.lca[(size_t)x * n + y] = iv; R.lca[(size_t)y * n + x] = iv; }
     }
-    // rows of the LCA matrix, run-length encoded: for b, the runs of constant lca(a,b) over a = 0 .. b-1 (they follow the
-    // ancestors of b from the root down, so there are at most depth(b) of them)
-    R.run_off.assign(n + 1, 0); R.run_end.clear(); R.run_pd.clear();
-    for (int b = 0; b < n; ++b) {
-        R.run_off[b] = (uint32_t)R.run_end.size();
-        for (int x = 0; x < b;) {
-            const uint16_t pnode = R.lca[(size_t)b * n + x];
-            int y = x + 1;
-            while (y < b && R.lca[(size_t)b * n + y] == pnode) ++y;
-            R.run_end.push_back((uint32_t)y);
-            R.run_pd.push_back((uint32_t)pnode | ((uint32_t)R.idepth[pnode] << 16));
-            x = y;
-        }
-    }
-    R.run_off[n] = (uint32_t)R.run_end.size();
     R.inner_parent.assign(R.n_inner, -1);
     for (int i = 0; i < R.n_inner; ++i) { const int v = R.inner_node[i]; if (v != 0) R.inner_parent[i] = R.inner_index[parent[v]]; }
     R.leaf_parent.assign(n, -1);
@@ -910,7 +893,7 @@ int scan_table(qs_ctx* c, const void* table, int dB, int dE, int count_scale) {
     for (uint16_t dd : c->ref.idepth) max_depth = std::max<int>(max_depth, dd + 1);
     a.q4_levels = std::min(max_depth, QS_Q4_MAX_LEVELS);
     if (const char* env = getenv("QS_SCAN_LEVELS")) a.q4_levels = std::max(2, std::min(QS_Q4_MAX_LEVELS, atoi(env)));       // test hook: force the deep (global-memory) path
-    a.run_off = c->d_run_off; a.run_end = c->d_run_end; a.run_pd = c->d_run_pd; a.inner_parent = c->d_inner_parent; a.leaf_parent = c->d_leaf_parent; a.inner_gap = c->d_inner_gap;
+    a.inner_parent = c->d_inner_parent; a.leaf_parent = c->d_leaf_parent; a.inner_gap = c->d_inner_gap;
     a.pair_sums = c->d_pair_sums; a.pair_best = c->d_pair_best; a.pair_score = c->d_pair_score; a.scratch = nullptr; a.work_counter = c->d_scan_counter;
     a.n = c->n; a.I = c->ref.n_inner;
     a.d_begin = dB; a.d_end = dE; a.count_scale = count_scale; a.cint_mask = cint_mask(c->cint_bytes);
@@ -1321,8 +1304,7 @@ int qs_set_reference(qs_ctx* ctx, int n_nodes, const int32_t* parent, const int3
             if (!v.empty() && cudaMemcpy(*dst, v.data(), v.size() * sizeof(v[0]), cudaMemcpyHostToDevice) != cudaSuccess) { ctx->err = "cudaMemcpy of the reference arrays failed"; return QS_E_CUDA; }
             return QS_OK;
         };
-        if ((r = up(&ctx->d_run_off, R.run_off)) || (r = up(&ctx->d_run_end, R.run_end)) || (r = up(&ctx->d_run_pd, R.run_pd)) ||
-            (r = up(&ctx->d_inner_parent, R.inner_parent)) || (r = up(&ctx->d_leaf_parent, R.leaf_parent)) || (r = up(&ctx->d_inner_gap, R.inner_gap)) || (r = up(&ctx->d_inner_node, R.inner_node)) ||
+        if ((r = up(&ctx->d_inner_parent, R.inner_parent)) || (r = up(&ctx->d_leaf_parent, R.leaf_parent)) || (r = up(&ctx->d_inner_gap, R.inner_gap)) || (r = up(&ctx->d_inner_node, R.inner_node)) ||
             (r = up(&ctx->d_node_parent, R.parent)) || (r = up(&ctx->d_node_depth, R.depth)) || (r = up(&ctx->d_node_edge, R.parent_edge)) ||
             (r = up(&ctx->d_node_inner, R.inner_index)))
             return r;
